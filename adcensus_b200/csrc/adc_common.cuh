@@ -1,0 +1,95 @@
+// adc_common.cuh -- shared declarations for the sm_100a AD-Census kernels.
+//
+// Data layout in HBM (per wave of S stereo pairs; every array is [S][...], pair index outermost):
+//   bgr      u8  [S][2][H][W][3]   left, right packed BGR exactly as the caller passes them
+//   gray     u8  [S][2][H][W]
+//   census   u64 [S][2][H][W]
+//   volA/B   f32 [S][H][W][Dp]     the two cost volumes, d fastest, Dp = D rounded up to 4 so that
+//                                  every pixel's disparity vector is a whole number of 128-bit words
+//   arms     u8x4[S][H][W]         left,right,top,bottom (cross_aggregator.h:17-20)
+//   sup_h/v  u16 [S][H][W]
+//   dmap     u8  [S][4][H][W]      colour-difference maps used by the scanline optimiser
+//   disp_*   f32 [S][H][W]
+//   label    u8  [S][H][W]         0 = valid, 1 = mismatch list, 2 = occlusion list
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define ADC_INVALID_F (__int_as_float(0x7f800000))  // +inf  (adcensus_types.h:33)
+#define ADC_LARGE_F 99999.0f                         // adcensus_types.h:35
+
+struct AdcDims {
+    int W, H, D, Dp;        // Dp: padded disparity stride (multiple of 4)
+    int dmin, dmax;
+    int N;                  // W*H
+    long long vol_stride;   // floats per pair volume = N*Dp
+};
+
+// Everything a kernel may need from ADCensusOption plus derived constants, passed by value.
+struct AdcParams {
+    AdcDims dm;
+    int L1, L2, t1, t2;          // cross arm parameters (L1 already clamped to 255)
+    float p1, p2, p1_4, p2_4, p1_10, p2_10;  // so_p1/so_p2 and their /4, /10 quotients (IEEE, host-computed)
+    int tso;
+    int irv_ts; float irv_th;
+    float lr_thres;
+    int max_search;              // max(|dmax|,|dmin|)
+};
+
+__device__ __forceinline__ int adc_colour_dist(uchar3 a, uchar3 b) {
+    int d0 = abs((int)a.x - (int)b.x), d1 = abs((int)a.y - (int)b.y), d2 = abs((int)a.z - (int)b.z);
+    return max(d0, max(d1, d2));
+}
+
+__device__ __forceinline__ uchar3 adc_load_bgr(const uint8_t* __restrict__ img, int idx) {
+    const uint8_t* p = img + 3ll * idx;
+    return make_uchar3(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+
+// order-preserving float -> uint key (any sign), for REDUX-based warp minima
+__device__ __forceinline__ unsigned adc_f2key(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float adc_key2f(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// ---- launchers (defined in the k_*.cu files; all asynchronous on `st`) -------------------------
+struct AdcWave {            // device pointers of one wave (S pairs)
+    int S;                  // active pairs in this launch
+    uint8_t* bgr;           // [S][2][N*3]
+    uint8_t* gray;          // [S][2][N]
+    unsigned long long* census; // [S][2][N]
+    float* volA; float* volB;
+    uchar4* arms;
+    uint16_t* sup_h; uint16_t* sup_v;
+    uint8_t* dmap;          // [S][4][N]: 0 = left-horizontal, 1 = left-vertical, 2 = right-horizontal, 3 = right-vertical
+    float* disp_l; float* disp_r; float* disp_t;
+    uint8_t* label; uint8_t* flag;
+    int* pend;              // [S][2][N] mismatch / occlusion pixel lists (raster order)
+    int* counters;          // [S][8]
+    const float* lut_ad;    // [766]  (1 - exp(-(s/3)/lambda_ad)) + 1, host libm expf
+    const float* lut_cen;   // [64]   exp(-h/lambda_census)
+    const double* ray_sin; const double* ray_cos; // [16] host libm sin/cos of the accumulated angles
+};
+
+void adc_launch_gray_census(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
+void adc_launch_cost(const AdcParams& P, const AdcWave& w, float* vol, cudaStream_t st, unsigned long long* launches);
+void adc_launch_diffmaps(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
+void adc_launch_arms(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
+// one 1-D pass of the cross aggregation: horizontal (dir=0) or vertical (dir=1) ordered sums,
+// optionally divided by the support count `sup` (second pass of an iteration)
+void adc_launch_arm_sum(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int dir,
+                        const uint16_t* sup, cudaStream_t st, unsigned long long* launches);
+// one scanline pass: (sx,sy) in {(1,0),(-1,0),(0,1),(0,-1)}
+int adc_launch_scanline(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
+                        cudaStream_t st, unsigned long long* launches);
+void adc_launch_wta(const AdcParams& P, const AdcWave& w, const float* vol, cudaStream_t st, unsigned long long* launches);
+void adc_launch_outlier(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
+void adc_launch_build_lists(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
+void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
+// k = 0: mismatch list, k = 1: occlusion list; reads disp_l, writes disp_t
+void adc_launch_interp_list(const AdcParams& P, const AdcWave& w, int k, cudaStream_t st, unsigned long long* launches);
+void adc_launch_discontinuity(const AdcParams& P, const AdcWave& w, const float* vol, cudaStream_t st, unsigned long long* launches);
+void adc_launch_median(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);

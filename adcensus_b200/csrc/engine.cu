@@ -1,0 +1,641 @@
+// engine.cu -- host side of the B200 AD-Census engine and its C ABI (include/adcensus_b200.h).
+//
+// An engine owns `lanes` independent pipelines.  A lane = one CUDA stream + a device arena for a
+// wave of up to `wave_pairs` stereo pairs (two cost volumes per pair dominate: 2*4*N*Dp bytes) +
+// pinned staging for callers that hand in pageable memory.  A batch is cut into waves that are
+// dealt round-robin to the lanes; every kernel of a wave is one batched launch over all its pairs
+// (pair index = outermost grid dimension), and the lanes overlap each other's copies, bandwidth
+// kernels and the latency-bound refinement kernels.  Nothing here ever falls back to a CPU path:
+// if the CUDA library cannot run, the call fails.
+#include <cuda_runtime.h>
+
+#include <math.h>
+#include <stdarg.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/adcensus_b200.h"
+#include "adc_common.cuh"
+
+static_assert(sizeof(adc_option) == 60, "adc_option must match the reference's ADCensusOption (60 bytes)");
+static_assert(offsetof(adc_option, so_p1) == 32 && offsetof(adc_option, irv_th) == 48 &&
+              offsetof(adc_option, do_lr_check) == 56 && offsetof(adc_option, do_discontinuity_adjustment) == 58,
+              "adc_option field offsets must match adcensus_types.h:45-75");
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t err__ = (call);                                                              \
+        if (err__ != cudaSuccess)                                                                \
+            return fail(ADC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    } while (0)
+
+struct Lane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev_done = nullptr;     // all work of the lane's latest wave (incl. D2H) finished
+    cudaEvent_t ev_in_free = nullptr;  // the H2D of the latest wave has consumed the staging-in buffer
+    void* arena = nullptr;
+    AdcWave w{};                       // device pointers, capacity S pairs
+    uint8_t* pin_in = nullptr;         // [S][2][N*3] pinned staging (pageable callers only)
+    float* pin_out = nullptr;          // [S][N]
+    // pending copy-out of a staged wave (pageable callers)
+    int drain_n = 0;
+    float* const* drain_ptrs = nullptr;
+    float* drain_base = nullptr;
+    int drain_first = 0;
+};
+
+}  // namespace
+
+struct adc_engine {
+    int W = 0, H = 0;
+    adc_option opt{};
+    adc_config cfg{};
+    AdcParams P{};
+    int S = 0;
+    std::vector<Lane> lanes;
+    cudaStream_t main_st = nullptr;
+    cudaEvent_t ev_fork = nullptr;
+    float* d_lut_ad = nullptr;
+    float* d_lut_cen = nullptr;
+    double* d_rays = nullptr;  // [32]: sin[16], cos[16]
+    unsigned long long launches = 0;
+    float stage_ms[6] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev_stage[8] = {};
+    // debug state (adc_debug_run): which buffer plays the reference's cost_init_ / cost_aggr_
+    const float* dbg_init = nullptr;
+    const float* dbg_aggr = nullptr;
+    int dbg_stage = -1;
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+    template <typename T> T* take(size_t count) {
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off = align_up(off + count * sizeof(T), 256);
+        return p;
+    }
+};
+
+// Carves (or, with base == nullptr, just sizes) one lane's arena.
+size_t carve_lane(void* base, const AdcDims& dm, int S, AdcWave* w) {
+    Carver c(base);
+    const size_t N = (size_t)dm.N;
+    AdcWave t{};
+    t.volA = c.take<float>((size_t)S * dm.vol_stride);
+    t.volB = c.take<float>((size_t)S * dm.vol_stride);
+    t.bgr = c.take<uint8_t>((size_t)S * 2 * N * 3);
+    t.gray = c.take<uint8_t>((size_t)S * 2 * N);
+    t.census = c.take<unsigned long long>((size_t)S * 2 * N);
+    t.arms = c.take<uchar4>((size_t)S * N);
+    t.sup_h = c.take<uint16_t>((size_t)S * N);
+    t.sup_v = c.take<uint16_t>((size_t)S * N);
+    t.dmap = c.take<uint8_t>((size_t)S * 4 * N);
+    t.disp_l = c.take<float>((size_t)S * N);
+    t.disp_r = c.take<float>((size_t)S * N);
+    t.disp_t = c.take<float>((size_t)S * N);
+    t.label = c.take<uint8_t>((size_t)S * N);
+    t.flag = c.take<uint8_t>((size_t)S * N);
+    t.pend = c.take<int>((size_t)S * 2 * N);
+    t.counters = c.take<int>((size_t)S * 8);
+    if (w) *w = t;
+    return c.off;
+}
+
+void build_params(adc_engine* e) {
+    const adc_option& o = e->opt;
+    AdcParams& P = e->P;
+    P.dm.W = e->W; P.dm.H = e->H;
+    P.dm.dmin = o.min_disparity; P.dm.dmax = o.max_disparity;
+    P.dm.D = o.max_disparity - o.min_disparity;
+    P.dm.Dp = (P.dm.D + 3) / 4 * 4;
+    P.dm.N = e->W * e->H;
+    P.dm.vol_stride = (long long)P.dm.N * P.dm.Dp;
+    P.L1 = std::min(o.cross_L1, 255);  // min(cross_L1_, MAX_ARM_LENGTH), cross_aggregator.cpp:151
+    P.L2 = o.cross_L2; P.t1 = o.cross_t1; P.t2 = o.cross_t2;
+    // scanline_optimizer.cpp:133-140: p/4 and p/10 are float / int -> IEEE float division
+    P.p1 = o.so_p1; P.p2 = o.so_p2;
+    P.p1_4 = o.so_p1 / 4; P.p2_4 = o.so_p2 / 4;
+    P.p1_10 = o.so_p1 / 10; P.p2_10 = o.so_p2 / 10;
+    P.tso = o.so_tso;
+    P.irv_ts = o.irv_ts; P.irv_th = o.irv_th;
+    P.lr_thres = o.lrcheck_thres;
+    P.max_search = std::max(abs(o.max_disparity), abs(o.min_disparity));  // multistep_refiner.cpp:236
+}
+
+int upload_tables(adc_engine* e) {
+    // exp() factors of the AD-census cost on their integer domains, with THIS host's libm expf and
+    // the reference's operation order (cost_computor.cpp:110-117): the device never calls exp.
+    std::vector<float> ad(766), cen(64);
+    for (int s = 0; s < 766; s++) {
+        const float cost_ad = (float)s / 3.0f;
+        const float e_ad = expf(-cost_ad / (float)e->opt.lambda_ad);
+        float t = 1.0f - e_ad;
+        t = t + 1.0f;
+        ad[s] = t;
+    }
+    for (int h = 0; h < 64; h++) cen[h] = expf(-(float)h / (float)e->opt.lambda_census);
+    // ray directions of ProperInterpolation (multistep_refiner.cpp:234,252-254,268)
+    double rays[32];
+    const float pi = 3.1415926f;
+    double ang = 0.0;
+    for (int s = 0; s < 16; s++) {
+        rays[s] = sin(ang);
+        rays[16 + s] = cos(ang);
+        ang += pi / 16;
+    }
+    CK(cudaMalloc(&e->d_lut_ad, sizeof(float) * 766));
+    CK(cudaMalloc(&e->d_lut_cen, sizeof(float) * 64));
+    CK(cudaMalloc(&e->d_rays, sizeof(double) * 32));
+    CK(cudaMemcpy(e->d_lut_ad, ad.data(), sizeof(float) * 766, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_lut_cen, cen.data(), sizeof(float) * 64, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_rays, rays, sizeof(double) * 32, cudaMemcpyHostToDevice));
+    return ADC_OK;
+}
+
+AdcWave wave_view(const adc_engine* e, const Lane& ln, int nS) {
+    AdcWave w = ln.w;
+    w.S = nS;
+    w.lut_ad = e->d_lut_ad;
+    w.lut_cen = e->d_lut_cen;
+    w.ray_sin = e->d_rays;
+    w.ray_cos = e->d_rays + 16;
+    return w;
+}
+
+// Enqueues the whole pipeline for the nS pairs whose images already sit in ln.w.bgr.  Stops after
+// `last_stage` (ADC_STAGE_MEDIAN = everything).  ev[] (optional, 6 events) are recorded at the
+// stage boundaries the reference times in Match (ADCensusStereo.cpp:81-129).
+int enqueue_pipeline(adc_engine* e, Lane& ln, int nS, int last_stage, cudaEvent_t* ev) {
+    const AdcParams& P = e->P;
+    const AdcWave w = wave_view(e, ln, nS);
+    cudaStream_t st = ln.st;
+    unsigned long long* L = &e->launches;
+    const size_t mapN = (size_t)nS * P.dm.N;
+    float* A = w.volA;
+    float* B = w.volB;
+    e->dbg_init = A;
+    e->dbg_aggr = A;
+    auto stop = [&](int stage) { e->dbg_stage = stage; return stage >= last_stage; };
+
+    // ---- stage 1: cost (cost_computor.cpp:123-137)
+    adc_launch_gray_census(P, w, st, L);
+    adc_launch_cost(P, w, A, st, L);
+    if (ev) CK(cudaEventRecord(ev[1], st));
+    if (stop(ADC_STAGE_COST)) return ADC_OK;
+
+    // ---- stage 2: arms, support counts, 4 aggregation iterations (cross_aggregator.cpp:89-118)
+    adc_launch_arms(P, w, st, L);
+    if (stop(ADC_STAGE_ARMS)) return ADC_OK;
+    for (int it = 0; it < 4; it++) {
+        const bool hfirst = (it % 2) == 0;  // H,V | V,H | H,V | V,H  (:102,116)
+        adc_launch_arm_sum(P, w, A, B, hfirst ? 0 : 1, nullptr, st, L);
+        adc_launch_arm_sum(P, w, B, A, hfirst ? 1 : 0, hfirst ? w.sup_h : w.sup_v, st, L);
+        if (stop(ADC_STAGE_AGG1 + it)) return ADC_OK;
+    }
+    if (ev) CK(cudaEventRecord(ev[2], st));
+
+    // ---- stage 3: scanline optimisation, 4 chained passes (scanline_optimizer.cpp:54-60)
+    adc_launch_diffmaps(P, w, st, L);
+    static const int dirs[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
+    for (int ps = 0; ps < 4; ps++) {
+        const float* src = (ps % 2 == 0) ? A : B;
+        float* dst = (ps % 2 == 0) ? B : A;
+        if (adc_launch_scanline(P, w, src, dst, dirs[ps][0], dirs[ps][1], st, L))
+            return fail(ADC_ERR_UNSUPPORTED, "disparity range %d exceeds the scanline kernel's limit of 256", P.dm.D);
+        if (ps % 2 == 0) e->dbg_init = B; else e->dbg_aggr = A;
+        if (stop(ADC_STAGE_SO1 + ps)) return ADC_OK;
+    }
+    if (ev) CK(cudaEventRecord(ev[3], st));
+
+    // ---- stage 4: left + right disparity (ADCensusStereo.cpp:108-109)
+    adc_launch_wta(P, w, A, st, L);
+    if (ev) CK(cudaEventRecord(ev[4], st));
+    if (stop(ADC_STAGE_WTA)) return ADC_OK;
+
+    // ---- stage 5: multi-step refinement (multistep_refiner.cpp:60-87)
+    if (e->opt.do_lr_check) {
+        adc_launch_outlier(P, w, st, L);  // disp_l (orig) -> disp_t, label
+        CK(cudaMemcpyAsync(w.disp_l, w.disp_t, mapN * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+        CK(cudaMemsetAsync(w.label, 0, mapN, st));
+        CK(cudaMemcpyAsync(w.disp_t, w.disp_l, mapN * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    if (stop(ADC_STAGE_OUTLIER)) return ADC_OK;
+    if (e->opt.do_filling) {  // gates voting AND interpolation (ADCensusStereo.cpp:183)
+        adc_launch_build_lists(P, w, st, L);
+        adc_launch_voting(P, w, st, L);
+        if (stop(ADC_STAGE_VOTE)) return ADC_OK;
+        for (int k = 0; k < 2; k++) {
+            adc_launch_interp_list(P, w, k, st, L);
+            CK(cudaMemcpyAsync(w.disp_l, w.disp_t, mapN * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+        if (stop(ADC_STAGE_INTERP)) return ADC_OK;
+    } else if (last_stage <= ADC_STAGE_INTERP) {
+        e->dbg_stage = last_stage;
+        return ADC_OK;
+    }
+    if (e->opt.do_discontinuity_adjustment) adc_launch_discontinuity(P, w, A, st, L);
+    if (stop(ADC_STAGE_DISC)) return ADC_OK;
+    adc_launch_median(P, w, st, L);
+    if (ev) CK(cudaEventRecord(ev[5], st));
+    e->dbg_stage = ADC_STAGE_MEDIAN;
+    CK(cudaGetLastError());
+    return ADC_OK;
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+int drain_lane(adc_engine* e, Lane& ln) {
+    if (ln.drain_n == 0) return ADC_OK;
+    CK(cudaEventSynchronize(ln.ev_done));
+    const size_t N = (size_t)e->P.dm.N;
+    for (int i = 0; i < ln.drain_n; i++) {
+        float* dst = ln.drain_ptrs ? ln.drain_ptrs[ln.drain_first + i] : ln.drain_base + (size_t)(ln.drain_first + i) * N;
+        memcpy(dst, ln.pin_out + (size_t)i * N, N * sizeof(float));
+    }
+    ln.drain_n = 0;
+    return ADC_OK;
+}
+
+enum SrcKind { SRC_HOST_PTRS, SRC_HOST_STRIDED, SRC_DEVICE_STRIDED };
+
+// Common batch driver.  `user` = stream to fork from / join to.
+int run_batch(adc_engine* e, int n, SrcKind kind, const uint8_t* const* lp, const uint8_t* const* rp,
+              float* const* dp, const uint8_t* ls, const uint8_t* rs, float* ds, cudaStream_t user, bool pinned) {
+    const size_t N = (size_t)e->P.dm.N, IMG = N * 3;
+    const int S = e->S, nl = (int)e->lanes.size();
+    CK(cudaEventRecord(e->ev_fork, user));
+    const int n_waves = (n + S - 1) / S;
+    for (int li = 0; li < std::min(nl, n_waves); li++) CK(cudaStreamWaitEvent(e->lanes[li].st, e->ev_fork, 0));
+    for (int wv = 0; wv < n_waves; wv++) {
+        Lane& ln = e->lanes[wv % nl];
+        const int first = wv * S, nS = std::min(S, n - first);
+        // ---- inputs -> ln.w.bgr  ([S][2][IMG])
+        if (kind == SRC_DEVICE_STRIDED) {
+            CK(cudaMemcpy2DAsync(ln.w.bgr, 2 * IMG, ls + (size_t)first * IMG, IMG, IMG, nS, cudaMemcpyDeviceToDevice, ln.st));
+            CK(cudaMemcpy2DAsync(ln.w.bgr + IMG, 2 * IMG, rs + (size_t)first * IMG, IMG, IMG, nS, cudaMemcpyDeviceToDevice, ln.st));
+        } else if (pinned) {
+            if (kind == SRC_HOST_STRIDED) {
+                CK(cudaMemcpy2DAsync(ln.w.bgr, 2 * IMG, ls + (size_t)first * IMG, IMG, IMG, nS, cudaMemcpyHostToDevice, ln.st));
+                CK(cudaMemcpy2DAsync(ln.w.bgr + IMG, 2 * IMG, rs + (size_t)first * IMG, IMG, IMG, nS, cudaMemcpyHostToDevice, ln.st));
+            } else {
+                for (int i = 0; i < nS; i++) {
+                    CK(cudaMemcpyAsync(ln.w.bgr + (size_t)i * 2 * IMG, lp[first + i], IMG, cudaMemcpyHostToDevice, ln.st));
+                    CK(cudaMemcpyAsync(ln.w.bgr + (size_t)i * 2 * IMG + IMG, rp[first + i], IMG, cudaMemcpyHostToDevice, ln.st));
+                }
+            }
+        } else {
+            // pageable caller memory: finish the lane's previous wave (copy-out), then stage through pinned memory
+            int rc = drain_lane(e, ln);
+            if (rc) return rc;
+            CK(cudaEventSynchronize(ln.ev_in_free));
+            for (int i = 0; i < nS; i++) {
+                const uint8_t* l = kind == SRC_HOST_PTRS ? lp[first + i] : ls + (size_t)(first + i) * IMG;
+                const uint8_t* r = kind == SRC_HOST_PTRS ? rp[first + i] : rs + (size_t)(first + i) * IMG;
+                memcpy(ln.pin_in + (size_t)i * 2 * IMG, l, IMG);
+                memcpy(ln.pin_in + (size_t)i * 2 * IMG + IMG, r, IMG);
+            }
+            CK(cudaMemcpyAsync(ln.w.bgr, ln.pin_in, (size_t)nS * 2 * IMG, cudaMemcpyHostToDevice, ln.st));
+            CK(cudaEventRecord(ln.ev_in_free, ln.st));
+        }
+        // ---- compute
+        int rc = enqueue_pipeline(e, ln, nS, ADC_STAGE_MEDIAN, nullptr);
+        if (rc) return rc;
+        // ---- outputs
+        if (kind == SRC_DEVICE_STRIDED) {
+            CK(cudaMemcpyAsync(ds + (size_t)first * N, ln.w.disp_l, (size_t)nS * N * sizeof(float), cudaMemcpyDeviceToDevice, ln.st));
+        } else if (pinned) {
+            if (kind == SRC_HOST_STRIDED) {
+                CK(cudaMemcpyAsync(ds + (size_t)first * N, ln.w.disp_l, (size_t)nS * N * sizeof(float), cudaMemcpyDeviceToHost, ln.st));
+            } else {
+                for (int i = 0; i < nS; i++)
+                    CK(cudaMemcpyAsync(dp[first + i], ln.w.disp_l + (size_t)i * N, N * sizeof(float), cudaMemcpyDeviceToHost, ln.st));
+            }
+        } else {
+            CK(cudaMemcpyAsync(ln.pin_out, ln.w.disp_l, (size_t)nS * N * sizeof(float), cudaMemcpyDeviceToHost, ln.st));
+            ln.drain_n = nS; ln.drain_first = first;
+            ln.drain_ptrs = kind == SRC_HOST_PTRS ? dp : nullptr;
+            ln.drain_base = ds;
+        }
+        CK(cudaEventRecord(ln.ev_done, ln.st));
+    }
+    for (int li = 0; li < std::min(nl, n_waves); li++) CK(cudaStreamWaitEvent(user, e->lanes[li].ev_done, 0));
+    if (!pinned && kind != SRC_DEVICE_STRIDED)
+        for (auto& ln : e->lanes) { int rc = drain_lane(e, ln); if (rc) return rc; }
+    return ADC_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* adc_last_error(void) { return g_err.c_str(); }
+const char* adc_version(void) { return "adcensus_b200 0.1 (sm_100a)"; }
+
+void adc_default_option(adc_option* o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->min_disparity = 0;  o->max_disparity = 64;
+    o->lambda_ad = 10;     o->lambda_census = 30;
+    o->cross_L1 = 34;      o->cross_L2 = 17;
+    o->cross_t1 = 20;      o->cross_t2 = 6;
+    o->so_p1 = 1.0f;       o->so_p2 = 3.0f;
+    o->so_tso = 15;        o->irv_ts = 20;
+    o->irv_th = 0.4f;      o->lrcheck_thres = 1.0f;
+    o->do_lr_check = 1;    o->do_filling = 1;
+    o->do_discontinuity_adjustment = 0;
+}
+
+void adc_destroy(adc_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto& ln : e->lanes) {
+        if (ln.arena) cudaFree(ln.arena);
+        if (ln.pin_in) cudaFreeHost(ln.pin_in);
+        if (ln.pin_out) cudaFreeHost(ln.pin_out);
+        if (ln.ev_done) cudaEventDestroy(ln.ev_done);
+        if (ln.ev_in_free) cudaEventDestroy(ln.ev_in_free);
+        if (ln.st) cudaStreamDestroy(ln.st);
+    }
+    if (e->d_lut_ad) cudaFree(e->d_lut_ad);
+    if (e->d_lut_cen) cudaFree(e->d_lut_cen);
+    if (e->d_rays) cudaFree(e->d_rays);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    for (auto& ev : e->ev_stage) if (ev) cudaEventDestroy(ev);
+    if (e->main_st) cudaStreamDestroy(e->main_st);
+    delete e;
+}
+
+int adc_create(int32_t width, int32_t height, const adc_option* opt, const adc_config* cfg, adc_engine** out) {
+    if (!out) return fail(ADC_ERR_ARG, "adc_create: out is NULL");
+    *out = nullptr;
+    if (!opt) return fail(ADC_ERR_ARG, "adc_create: option is NULL");
+    if (width <= 0 || height <= 0) return fail(ADC_ERR_ARG, "adc_create: non-positive image size %dx%d", width, height);
+    if (opt->max_disparity - opt->min_disparity <= 0)
+        return fail(ADC_ERR_ARG, "adc_create: empty disparity range [%d,%d)", opt->min_disparity, opt->max_disparity);
+    if ((long long)width * height > (1ll << 28)) return fail(ADC_ERR_UNSUPPORTED, "adc_create: image too large");
+    if (opt->max_disparity - opt->min_disparity > 256)
+        return fail(ADC_ERR_UNSUPPORTED, "adc_create: disparity range %d > 256 is not supported", opt->max_disparity - opt->min_disparity);
+
+    adc_engine* e = new adc_engine();
+    e->W = width; e->H = height; e->opt = *opt;
+    if (cfg) e->cfg = *cfg;
+    build_params(e);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        delete e;
+        return fail(ADC_ERR_CUDA, "adc_create: no CUDA device available (this library has no CPU fallback)");
+    }
+    if (e->cfg.device < 0 || e->cfg.device >= ndev) { delete e; return fail(ADC_ERR_ARG, "adc_create: bad device ordinal"); }
+    auto bail = [&](int rc) { adc_destroy(e); return rc; };
+    if (cudaSetDevice(e->cfg.device) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "cudaSetDevice failed"));
+
+    // wave size: enough scanlines in flight for the warp-per-line scanline kernels (~3k lines)
+    int S = e->cfg.wave_pairs;
+    if (S <= 0) S = std::min(16, std::max(2, (3072 + std::min(width, height) - 1) / std::min(width, height)));
+    int nl = e->cfg.lanes > 0 ? e->cfg.lanes : 3;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "cudaMemGetInfo failed"));
+    while (true) {
+        const size_t need = carve_lane(nullptr, e->P.dm, S, nullptr) * nl;
+        if (need < free_b * 8 / 10) break;
+        if (nl > 1) nl--; else if (S > 1) S--; else return bail(fail(ADC_ERR_NOMEM, "adc_create: one pair does not fit in device memory"));
+    }
+    e->S = S;
+    e->cfg.wave_pairs = S; e->cfg.lanes = nl;
+
+    int rc = upload_tables(e);
+    if (rc) return bail(rc);
+    if (cudaStreamCreateWithFlags(&e->main_st, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "stream create failed"));
+    if (cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "event create failed"));
+    for (auto& ev : e->ev_stage) if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "event create failed"));
+    e->lanes.resize(nl);
+    const size_t N = (size_t)e->P.dm.N;
+    for (auto& ln : e->lanes) {
+        if (cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "stream create failed"));
+        if (cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "event create failed"));
+        if (cudaEventCreateWithFlags(&ln.ev_in_free, cudaEventDisableTiming) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "event create failed"));
+        const size_t bytes = carve_lane(nullptr, e->P.dm, S, nullptr);
+        if (cudaMalloc(&ln.arena, bytes) != cudaSuccess) { cudaGetLastError(); return bail(fail(ADC_ERR_NOMEM, "device arena of %zu bytes", bytes)); }
+        carve_lane(ln.arena, e->P.dm, S, &ln.w);
+        if (cudaMemsetAsync(ln.arena, 0, bytes, ln.st) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "memset failed"));
+        if (cudaHostAlloc((void**)&ln.pin_in, (size_t)S * 2 * N * 3, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void**)&ln.pin_out, (size_t)S * N * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return bail(fail(ADC_ERR_NOMEM, "pinned staging allocation failed"));
+        }
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "device sync failed: %s", cudaGetErrorString(cudaGetLastError())));
+    *out = e;
+    return ADC_OK;
+}
+
+int adc_match(adc_engine* e, const uint8_t* img_left, const uint8_t* img_right, float* disp_left) {
+    if (!e) return fail(ADC_ERR_ARG, "adc_match: engine is NULL (Match before Initialize)");
+    if (!img_left || !img_right || !disp_left) return fail(ADC_ERR_ARG, "adc_match: NULL image or output pointer");
+    CK(cudaSetDevice(e->cfg.device));
+    Lane& ln = e->lanes[0];
+    const size_t N = (size_t)e->P.dm.N, IMG = N * 3;
+    int rc = drain_lane(e, ln);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ln.st));
+    memcpy(ln.pin_in, img_left, IMG);
+    memcpy(ln.pin_in + IMG, img_right, IMG);
+    CK(cudaEventRecord(e->ev_stage[0], ln.st));
+    CK(cudaMemcpyAsync(ln.w.bgr, ln.pin_in, 2 * IMG, cudaMemcpyHostToDevice, ln.st));
+    rc = enqueue_pipeline(e, ln, 1, ADC_STAGE_MEDIAN, e->ev_stage);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ln.pin_out, ln.w.disp_l, N * sizeof(float), cudaMemcpyDeviceToHost, ln.st));
+    CK(cudaEventRecord(e->ev_stage[6], ln.st));
+    CK(cudaStreamSynchronize(ln.st));
+    memcpy(disp_left, ln.pin_out, N * sizeof(float));
+    for (int i = 0; i < 6; i++) CK(cudaEventElapsedTime(&e->stage_ms[i], e->ev_stage[i], e->ev_stage[i + 1]));
+    return ADC_OK;
+}
+
+int adc_match_batch(adc_engine* e, int32_t n, const uint8_t* const* img_left, const uint8_t* const* img_right,
+                    float* const* disp_left) {
+    if (!e) return fail(ADC_ERR_ARG, "adc_match_batch: engine is NULL");
+    if (n < 0 || (n > 0 && (!img_left || !img_right || !disp_left))) return fail(ADC_ERR_ARG, "adc_match_batch: bad arguments");
+    if (n == 0) return ADC_OK;
+    bool pinned = true;
+    for (int i = 0; i < n; i++) {
+        if (!img_left[i] || !img_right[i] || !disp_left[i]) return fail(ADC_ERR_ARG, "adc_match_batch: NULL pointer for pair %d", i);
+    }
+    CK(cudaSetDevice(e->cfg.device));
+    for (int i = 0; i < n && pinned; i++) pinned = is_pinned(img_left[i]) && is_pinned(img_right[i]) && is_pinned(disp_left[i]);
+    int rc = run_batch(e, n, SRC_HOST_PTRS, img_left, img_right, disp_left, nullptr, nullptr, nullptr, e->main_st, pinned);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(e->main_st));
+    return ADC_OK;
+}
+
+int adc_match_batch_strided(adc_engine* e, int32_t n, const uint8_t* left, const uint8_t* right, float* disp) {
+    if (!e) return fail(ADC_ERR_ARG, "adc_match_batch_strided: engine is NULL");
+    if (n < 0 || (n > 0 && (!left || !right || !disp))) return fail(ADC_ERR_ARG, "adc_match_batch_strided: bad arguments");
+    if (n == 0) return ADC_OK;
+    CK(cudaSetDevice(e->cfg.device));
+    const bool pinned = is_pinned(left) && is_pinned(right) && is_pinned(disp);
+    int rc = run_batch(e, n, SRC_HOST_STRIDED, nullptr, nullptr, nullptr, left, right, disp, e->main_st, pinned);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(e->main_st));
+    return ADC_OK;
+}
+
+int adc_match_batch_pinned_async(adc_engine* e, int32_t n, const uint8_t* left, const uint8_t* right, float* disp, void* stream) {
+    if (!e) return fail(ADC_ERR_ARG, "adc_match_batch_pinned_async: engine is NULL");
+    if (n < 0 || (n > 0 && (!left || !right || !disp))) return fail(ADC_ERR_ARG, "adc_match_batch_pinned_async: bad arguments");
+    if (n == 0) return ADC_OK;
+    CK(cudaSetDevice(e->cfg.device));
+    if (!(is_pinned(left) && is_pinned(right) && is_pinned(disp)))
+        return fail(ADC_ERR_ARG, "adc_match_batch_pinned_async: buffers must be pinned host memory");
+    return run_batch(e, n, SRC_HOST_STRIDED, nullptr, nullptr, nullptr, left, right, disp, (cudaStream_t)stream, true);
+}
+
+int adc_match_batch_device(adc_engine* e, int32_t n, const uint8_t* d_left, const uint8_t* d_right, float* d_disp, void* stream) {
+    if (!e) return fail(ADC_ERR_ARG, "adc_match_batch_device: engine is NULL");
+    if (n < 0 || (n > 0 && (!d_left || !d_right || !d_disp))) return fail(ADC_ERR_ARG, "adc_match_batch_device: bad arguments");
+    if (n == 0) return ADC_OK;
+    CK(cudaSetDevice(e->cfg.device));
+    return run_batch(e, n, SRC_DEVICE_STRIDED, nullptr, nullptr, nullptr, d_left, d_right, d_disp, (cudaStream_t)stream, true);
+}
+
+void* adc_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void adc_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int adc_synchronize(adc_engine* e) {
+    if (!e) return fail(ADC_ERR_ARG, "adc_synchronize: engine is NULL");
+    CK(cudaSetDevice(e->cfg.device));
+    for (auto& ln : e->lanes) CK(cudaStreamSynchronize(ln.st));
+    CK(cudaStreamSynchronize(e->main_st));
+    return ADC_OK;
+}
+
+uint64_t adc_launch_count(const adc_engine* e) { return e ? e->launches : 0; }
+
+int adc_last_stage_ms(const adc_engine* e, float out[6]) {
+    if (!e || !out) return fail(ADC_ERR_ARG, "adc_last_stage_ms: bad arguments");
+    // ev_stage[0..6]: start | cost | aggregation | scanline | wta | refine | output copy
+    for (int i = 0; i < 6; i++) out[i] = e->stage_ms[i];
+    return ADC_OK;
+}
+
+int adc_get_config(const adc_engine* e, adc_config* out) {
+    if (!e || !out) return fail(ADC_ERR_ARG, "adc_get_config: bad arguments");
+    *out = e->cfg;
+    return ADC_OK;
+}
+
+// ---- debug taps -----------------------------------------------------------------------------
+int adc_debug_run(adc_engine* e, const uint8_t* img_left, const uint8_t* img_right, int32_t last_stage) {
+    if (!e) return fail(ADC_ERR_ARG, "adc_debug_run: engine is NULL");
+    if (!img_left || !img_right) return fail(ADC_ERR_ARG, "adc_debug_run: NULL image");
+    if (last_stage < 0 || last_stage >= ADC_STAGE_COUNT) return fail(ADC_ERR_ARG, "adc_debug_run: bad stage");
+    CK(cudaSetDevice(e->cfg.device));
+    Lane& ln = e->lanes[0];
+    const size_t IMG = (size_t)e->P.dm.N * 3;
+    int rc = drain_lane(e, ln);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ln.st));
+    CK(cudaMemcpyAsync(ln.w.bgr, img_left, IMG, cudaMemcpyHostToDevice, ln.st));
+    CK(cudaMemcpyAsync(ln.w.bgr + IMG, img_right, IMG, cudaMemcpyHostToDevice, ln.st));
+    rc = enqueue_pipeline(e, ln, 1, last_stage, nullptr);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ln.st));
+    CK(cudaGetLastError());
+    return ADC_OK;
+}
+
+size_t adc_debug_get(adc_engine* e, int32_t tap, void* dst, size_t cap) {
+    if (!e) { fail(ADC_ERR_ARG, "adc_debug_get: engine is NULL"); return 0; }
+    if (cudaSetDevice(e->cfg.device) != cudaSuccess) return 0;
+    const AdcDims& dm = e->P.dm;
+    const Lane& ln = e->lanes[0];
+    const size_t N = (size_t)dm.N;
+    const void* src = nullptr;
+    size_t bytes = 0;
+    switch (tap) {
+        case ADC_TAP_GRAY_L: src = ln.w.gray; bytes = N; break;
+        case ADC_TAP_GRAY_R: src = ln.w.gray + N; bytes = N; break;
+        case ADC_TAP_CENSUS_L: src = ln.w.census; bytes = N * 8; break;
+        case ADC_TAP_CENSUS_R: src = ln.w.census + N; bytes = N * 8; break;
+        case ADC_TAP_ARMS: src = ln.w.arms; bytes = N * 4; break;
+        case ADC_TAP_SUPCNT_H: src = ln.w.sup_h; bytes = N * 2; break;
+        case ADC_TAP_SUPCNT_V: src = ln.w.sup_v; bytes = N * 2; break;
+        case ADC_TAP_DISP_L: src = ln.w.disp_l; bytes = N * 4; break;
+        case ADC_TAP_DISP_R: src = ln.w.disp_r; bytes = N * 4; break;
+        case ADC_TAP_VOL_INIT:
+        case ADC_TAP_VOL_AGGR: {
+            const float* v = tap == ADC_TAP_VOL_INIT ? e->dbg_init : e->dbg_aggr;
+            bytes = N * dm.D * sizeof(float);
+            if (!dst || cap < bytes || !v) return bytes;
+            // strip the Dp padding: [N][Dp] -> [N][D]
+            if (cudaMemcpy2D(dst, (size_t)dm.D * 4, v, (size_t)dm.Dp * 4, (size_t)dm.D * 4, N, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                fail(ADC_ERR_CUDA, "adc_debug_get: copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return 0;
+            }
+            return bytes;
+        }
+        case ADC_TAP_MISMATCHES:
+        case ADC_TAP_OCCLUSIONS: {
+            // the lists are the pixels labelled 1 / 2, in raster order (the reference builds them by a
+            // raster scan and only ever erases from them)
+            std::vector<uint8_t> lab(N);
+            if (cudaMemcpy(lab.data(), ln.w.label, N, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+            const uint8_t want = tap == ADC_TAP_MISMATCHES ? 1 : 2;
+            size_t cnt = 0;
+            for (size_t i = 0; i < N; i++) cnt += lab[i] == want;
+            bytes = cnt * 8;
+            if (!dst || cap < bytes) return bytes;
+            int32_t* o = static_cast<int32_t*>(dst);
+            for (size_t i = 0; i < N; i++)
+                if (lab[i] == want) { *o++ = (int32_t)(i % dm.W); *o++ = (int32_t)(i / dm.W); }
+            return bytes;
+        }
+        default: fail(ADC_ERR_ARG, "adc_debug_get: unknown tap %d", tap); return 0;
+    }
+    if (!dst || cap < bytes) return bytes;
+    if (cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        fail(ADC_ERR_CUDA, "adc_debug_get: copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    return bytes;
+}
+
+}  // extern "C"

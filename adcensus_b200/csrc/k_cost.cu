@@ -1,0 +1,143 @@
+// k_cost.cu -- stage 1 of the pipeline: gray conversion, 9x7 census transform and the AD-census
+// cost volume (reference: cost_computor.cpp:58-121, adcensus_util.cpp:10-53), plus the colour
+// difference maps the scanline optimiser consumes (scanline_optimizer.cpp:113-121, 224-235).
+#include "adc_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// gray + census.  One CTA = 32x8 output pixels of one image; the (8+8)x(32+6) gray tile lives in
+// shared memory so each gray value is converted once and compared 63 times from on-chip memory.
+// Gray is double precision without contraction (r*0.299 + g*0.587 + b*0.114, truncated), which is
+// what cost_computor.cpp:69 evaluates; FMA contraction would flip 2933 of the 2^24 inputs.
+// ---------------------------------------------------------------------------------------------
+#define CT_W 32
+#define CT_H 8
+#define CT_HX 3
+#define CT_HY 4
+
+__device__ __forceinline__ uint8_t gray_of(const uint8_t* __restrict__ px) {
+    const double b = (double)__ldg(px), g = (double)__ldg(px + 1), r = (double)__ldg(px + 2);
+    const double v = __dadd_rn(__dadd_rn(__dmul_rn(r, 0.299), __dmul_rn(g, 0.587)), __dmul_rn(b, 0.114));
+    return (uint8_t)__double2int_rz(v);
+}
+
+__global__ void __launch_bounds__(CT_W* CT_H)
+k_gray_census(AdcDims dm, const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray,
+              unsigned long long* __restrict__ census) {
+    __shared__ uint8_t tile[CT_H + 2 * CT_HY][CT_W + 2 * CT_HX + 2];
+    const int img = blockIdx.z;  // pair*2 + view
+    const uint8_t* src = bgr + (size_t)img * dm.N * 3;
+    uint8_t* g_out = gray + (size_t)img * dm.N;
+    unsigned long long* c_out = census + (size_t)img * dm.N;
+    const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+    const int tid = threadIdx.y * CT_W + threadIdx.x;
+    constexpr int TW = CT_W + 2 * CT_HX, TH = CT_H + 2 * CT_HY;
+    for (int i = tid; i < TW * TH; i += CT_W * CT_H) {
+        const int ty = i / TW, tx = i - ty * TW;
+        const int gx = x0 + tx - CT_HX, gy = y0 + ty - CT_HY;
+        uint8_t v = 0;
+        if (gx >= 0 && gx < dm.W && gy >= 0 && gy < dm.H) v = gray_of(src + ((size_t)gy * dm.W + gx) * 3);
+        tile[ty][tx] = v;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= dm.W || y >= dm.H) return;
+    const int tx = threadIdx.x + CT_HX, ty = threadIdx.y + CT_HY;
+    const uint8_t centre = tile[ty][tx];
+    g_out[(size_t)y * dm.W + x] = centre;
+    unsigned long long bits = 0ull;
+    // border pixels keep 0 and tiny images are skipped entirely (adcensus_util.cpp:12,17-18)
+    if (dm.W > 9 && dm.H > 7 && y >= 4 && y < dm.H - 4 && x >= 3 && x < dm.W - 3) {
+#pragma unroll
+        for (int dy = -CT_HY; dy <= CT_HY; dy++)
+#pragma unroll
+            for (int dx = -CT_HX; dx <= CT_HX; dx++)
+                bits = (bits << 1) | (unsigned long long)(tile[ty + dy][tx + dx] < centre);
+    }
+    c_out[(size_t)y * dm.W + x] = bits;
+}
+
+void adc_launch_gray_census(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
+    dim3 grid((P.dm.W + CT_W - 1) / CT_W, (P.dm.H + CT_H - 1) / CT_H, w.S * 2), block(CT_W, CT_H);
+    k_gray_census<<<grid, block, 0, st>>>(P.dm, w.bgr, w.gray, w.census);
+    ++*launches;
+}
+
+// ---------------------------------------------------------------------------------------------
+// AD-census cost volume.  One thread = one pixel x four consecutive disparities -> one 128-bit
+// store; consecutive threads cover consecutive disparity quads of the same pixel, then the next
+// pixel, so a warp writes 512 contiguous bytes.  The two exp() factors have tiny integer domains
+// (sum of abs differences 0..765, Hamming 0..63): they come from tables built on the host with the
+// host's libm expf, evaluated in the reference's order  ((1 - e_ad) + 1) - e_cen
+// (cost_computor.cpp:110-117), so the volume is bit-identical to the CPU path by construction.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_cost_volume(AdcDims dm, int px_per_block, const uint8_t* __restrict__ bgr,
+              const unsigned long long* __restrict__ census, float* __restrict__ vol,
+              const float* __restrict__ lut_ad, const float* __restrict__ lut_cen) {
+    const int pair = blockIdx.z;
+    const int y = blockIdx.y;
+    const int Q = dm.Dp >> 2;
+    const int p = threadIdx.x / Q, q = threadIdx.x - p * Q;
+    const int x = blockIdx.x * px_per_block + p;
+    if (p >= px_per_block || x >= dm.W) return;
+    const uint8_t* left = bgr + (size_t)pair * 2 * dm.N * 3;
+    const uint8_t* right = left + (size_t)dm.N * 3;
+    const unsigned long long* cen_l = census + (size_t)pair * 2 * dm.N;
+    const unsigned long long* cen_r = cen_l + dm.N;
+    const int row = y * dm.W;
+    const uchar3 cl = adc_load_bgr(left, row + x);
+    const unsigned long long bl = __ldg(cen_l + row + x);
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int di = 4 * q + j;
+        const int xr = x - (dm.dmin + di);
+        float c = 1.0f;  // out-of-image match: cost_computor.cpp:101-104
+        if (di >= dm.D) c = 0.0f;  // padding lane, never read as a cost
+        else if (xr >= 0 && xr < dm.W) {
+            const uchar3 cr = adc_load_bgr(right, row + xr);
+            const int sad = abs((int)cl.x - (int)cr.x) + abs((int)cl.y - (int)cr.y) + abs((int)cl.z - (int)cr.z);
+            const int ham = __popcll(bl ^ __ldg(cen_r + row + xr));
+            c = __fsub_rn(__ldg(lut_ad + sad), __ldg(lut_cen + ham));
+        }
+        out[j] = c;
+    }
+    float4* dst = reinterpret_cast<float4*>(vol + (size_t)pair * dm.vol_stride + ((size_t)row + x) * dm.Dp) + q;
+    *dst = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+void adc_launch_cost(const AdcParams& P, const AdcWave& w, float* vol, cudaStream_t st, unsigned long long* launches) {
+    const int Q = P.dm.Dp / 4;
+    int ppb = 256 / Q;
+    if (ppb < 1) ppb = 1;
+    int threads = ppb * Q;
+    dim3 grid((P.dm.W + ppb - 1) / ppb, P.dm.H, w.S);
+    k_cost_volume<<<grid, threads, 0, st>>>(P.dm, ppb, w.bgr, w.census, vol, w.lut_ad, w.lut_cen);
+    ++*launches;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Colour-difference maps for the scanline optimiser: max-channel distance between a pixel and
+// its predecessor along x (h) or y (v), for the left and the right image.  A forward pass reads
+// map[cur]; a backward pass reads map[pixel it came from] (same two pixels, see k_scanline.cu).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_diffmaps(AdcDims dm, const uint8_t* __restrict__ bgr, uint8_t* __restrict__ dmap) {
+    const int pair = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dm.N) return;
+    const int y = i / dm.W, x = i - y * dm.W;
+    uint8_t* out = dmap + (size_t)pair * 4 * dm.N;
+#pragma unroll
+    for (int v = 0; v < 2; v++) {
+        const uint8_t* img = bgr + ((size_t)pair * 2 + v) * dm.N * 3;
+        const uchar3 c = adc_load_bgr(img, i);
+        out[(size_t)(2 * v) * dm.N + i] = x > 0 ? (uint8_t)adc_colour_dist(c, adc_load_bgr(img, i - 1)) : 0;
+        out[(size_t)(2 * v + 1) * dm.N + i] = y > 0 ? (uint8_t)adc_colour_dist(c, adc_load_bgr(img, i - dm.W)) : 0;
+    }
+}
+
+void adc_launch_diffmaps(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
+    dim3 grid((P.dm.N + 255) / 256, w.S);
+    k_diffmaps<<<grid, 256, 0, st>>>(P.dm, w.bgr, w.dmap);
+    ++*launches;
+}

@@ -1,0 +1,440 @@
+// k_refine.cu -- stage 5: multi-step disparity refinement (reference: multistep_refiner.cpp:60-87):
+// LR-check outlier detection (:90-151), iterative region voting (:153-227), 16-ray proper
+// interpolation (:229-305), optional depth-discontinuity adjustment (:307-371) and the in-place 3x3
+// median (adcensus_util.cpp:55-81 called with in == out at multistep_refiner.cpp:86).
+//
+// The reference runs all of these sequentially *in place*, and the in-place order is part of the
+// answer.  Each kernel below is a parallel schedule that provably reproduces the sequential
+// result (argument given at each kernel); none of them approximates.
+#include "adc_common.cuh"
+
+// =============================================================================================
+// 1. Outlier detection.  The raster scan reads disp_left[col_rl] of the same row while already
+//    having invalidated pixels to the left of x.  Whether a pixel gets invalidated depends only on
+//    the ORIGINAL maps (its own disparity and the right map), so: phase 1 computes that predicate
+//    for every pixel; phase 2 classifies, seeing +inf for col_rl < x that phase 1 marked, and the
+//    original value otherwise (col_rl == x reads the pixel itself before it is invalidated).
+// =============================================================================================
+__global__ void k_outlier_mark(AdcParams P, const float* __restrict__ disp_l, const float* __restrict__ disp_r,
+                               uint8_t* __restrict__ flag) {
+    const AdcDims& dm = P.dm;
+    const int pair = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dm.N) return;
+    const int y = i / dm.W, x = i - y * dm.W;
+    const float d = disp_l[(size_t)pair * dm.N + i];
+    uint8_t f = 0;
+    if (d == ADC_INVALID_F) f = 1;
+    else {
+        const long col_r = lroundf(__fsub_rn((float)x, d));
+        if (col_r < 0 || col_r >= dm.W) f = 1;
+        else {
+            const float dr = disp_r[(size_t)pair * dm.N + y * dm.W + col_r];
+            if (fabsf(__fsub_rn(d, dr)) > P.lr_thres) f = 2;
+        }
+    }
+    flag[(size_t)pair * dm.N + i] = f;
+}
+
+__global__ void k_outlier_classify(AdcParams P, const float* __restrict__ disp_l, const float* __restrict__ disp_r,
+                                   const uint8_t* __restrict__ flag, float* __restrict__ disp_out,
+                                   uint8_t* __restrict__ label) {
+    const AdcDims& dm = P.dm;
+    const int pair = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dm.N) return;
+    const size_t o = (size_t)pair * dm.N;
+    const int y = i / dm.W, x = i - y * dm.W;
+    const uint8_t f = flag[o + i];
+    const float d = disp_l[o + i];
+    uint8_t lab = 0;
+    if (f == 1) lab = 1;
+    else if (f == 2) {
+        const long col_r = lroundf(__fsub_rn((float)x, d));
+        const float dr = disp_r[o + y * dm.W + col_r];
+        const int col_rl = (int)lroundf(__fadd_rn((float)col_r, dr));
+        lab = 1;
+        if (col_rl > 0 && col_rl < dm.W) {
+            const int j = y * dm.W + col_rl;
+            const float dl = (col_rl < x && flag[o + j] != 0) ? ADC_INVALID_F : disp_l[o + j];
+            if (dl > d) lab = 2;
+        }
+    }
+    label[o + i] = lab;
+    disp_out[o + i] = f ? ADC_INVALID_F : d;
+}
+
+void adc_launch_outlier(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
+    dim3 grid((P.dm.N + 255) / 256, w.S);
+    k_outlier_mark<<<grid, 256, 0, st>>>(P, w.disp_l, w.disp_r, w.flag);
+    k_outlier_classify<<<grid, 256, 0, st>>>(P, w.disp_l, w.disp_r, w.flag, w.disp_t, w.label);
+    *launches += 2;
+}
+
+// =============================================================================================
+// 2. Iterative region voting.  Reference: 5 iterations x {mismatch list, occlusion list}; within a
+//    sweep pixels are visited in list (= raster) order and a filled pixel is immediately visible to
+//    later ones (Gauss-Seidel).  Exact parallel form ("raster-aware fixed point"): keep OLD (state at
+//    sweep start) and NEW.  Repeatedly recompute every pending pixel p of the list in parallel,
+//    reading neighbour q from NEW if q precedes p in raster order and from OLD otherwise, until a
+//    full round changes nothing.  The sequential result is the unique fixed point of that map (by
+//    induction over raster order: the first pending pixel only depends on OLD, pixel p only on OLD
+//    and on earlier pixels), so ANY asynchronous evaluation order converges to it; a round that
+//    changes nothing was computed entirely from settled values and therefore certifies it.
+//    One CTA per stereo pair; the batch supplies the parallelism across SMs.
+// =============================================================================================
+#define RV_THREADS 1024
+#define RV_WARPS (RV_THREADS / 32)
+#define RV_MAXD 256
+
+// ordered compaction of `n_in` candidates (keep[i] decided by the caller's lambda) -- helper
+template <typename KeepFn, typename ValFn>
+__device__ int rv_compact(int n_in, int* __restrict__ out, KeepFn keep, ValFn val, int* s_warp_tot) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int base = 0;
+    for (int start = 0; start < n_in; start += RV_THREADS) {
+        const int i = start + tid;
+        int v = 0;
+        bool k = false;
+        if (i < n_in) { v = val(i); k = keep(i, v); }
+        const unsigned b = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) s_warp_tot[wid] = __popc(b);
+        __syncthreads();  // also orders this chunk's reads before its writes (in-place compaction)
+        int off = base, tot = 0;
+        for (int w2 = 0; w2 < RV_WARPS; w2++) {
+            const int c = s_warp_tot[w2];
+            if (w2 < wid) off += c;
+            tot += c;
+        }
+        if (k) out[off + __popc(b & ((1u << lane) - 1u))] = v;
+        base += tot;
+        __syncthreads();
+    }
+    return base;
+}
+
+__global__ void __launch_bounds__(RV_THREADS)
+k_build_lists(AdcDims dm, const uint8_t* __restrict__ label, int* __restrict__ pend, int* __restrict__ counters) {
+    __shared__ int s_tot[RV_WARPS];
+    const int pair = blockIdx.x;
+    const uint8_t* lab = label + (size_t)pair * dm.N;
+    for (int k = 0; k < 2; k++) {
+        int* list = pend + ((size_t)pair * 2 + k) * dm.N;
+        const int n = rv_compact(dm.N, list, [&](int i, int) { return lab[i] == k + 1; }, [&](int i) { return i; }, s_tot);
+        if (threadIdx.x == 0) counters[pair * 8 + k] = n;
+    }
+}
+
+__global__ void __launch_bounds__(RV_THREADS)
+k_region_voting(AdcParams P, const uchar4* __restrict__ arms, float* disp_old, float* disp_new,
+                uint8_t* __restrict__ label, int* __restrict__ pend, int* __restrict__ counters) {
+    __shared__ int s_hist[RV_WARPS][RV_MAXD];
+    __shared__ int s_tot[RV_WARPS];
+    __shared__ int s_changed;
+    const AdcDims& dm = P.dm;
+    const int pair = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int W = dm.W, D = dm.D;
+    const uchar4* A = arms + (size_t)pair * dm.N;
+    float* d_old = disp_old + (size_t)pair * dm.N;
+    float* d_new = disp_new + (size_t)pair * dm.N;
+    uint8_t* lab = label + (size_t)pair * dm.N;
+    int n_list[2] = {counters[pair * 8 + 0], counters[pair * 8 + 1]};
+    int rounds_total = 0;
+    int* hist = s_hist[wid];
+    const int grp = lane >> 3, sub = lane & 7;
+
+    for (int it = 0; it < 5; it++) {
+        for (int k = 0; k < 2; k++) {
+            int* list = pend + ((size_t)pair * 2 + k) * dm.N;
+            const int n = n_list[k];
+            if (n == 0) continue;  // uniform across the CTA
+            // ---- rounds until a full pass changes nothing
+            while (true) {
+                if (tid == 0) s_changed = 0;
+                __syncthreads();
+                for (int idx = wid; idx < n; idx += RV_WARPS) {
+                    const int p = list[idx];
+                    const int y = p / W, x = p - y * W;
+                    for (int b = lane; b < D; b += 32) hist[b] = 0;
+                    __syncwarp();
+                    const uchar4 a = __ldg(A + p);
+                    for (int t = -(int)a.z + grp; t <= (int)a.w; t += 4) {
+                        const int rowi = (y + t) * W + x;
+                        const uchar4 a2 = __ldg(A + rowi);
+                        for (int s = -(int)a2.x + sub; s <= (int)a2.y; s += 8) {
+                            const bool before = (t < 0) || (t == 0 && s < 0);
+                            const float d = before ? __ldcg(d_new + rowi + s) : __ldcg(d_old + rowi + s);
+                            if (d != ADC_INVALID_F) {
+                                const long di = lroundf(d) - dm.dmin;
+                                if (di >= 0 && di < D) atomicAdd(&hist[di], 1);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    int peak = 0, best = 0x7fffffff, total = 0;
+                    for (int b = lane; b < D; b += 32) {
+                        const int h = hist[b];
+                        if (peak < h) { peak = h; best = b; }
+                        total += h;
+                    }
+                    const int gpeak = __reduce_max_sync(0xffffffffu, peak);
+                    const int gbest = __reduce_min_sync(0xffffffffu, peak == gpeak ? best : 0x7fffffff);
+                    total = __reduce_add_sync(0xffffffffu, total);
+                    __syncwarp();
+                    if (lane == 0) {
+                        float r = ADC_INVALID_F;
+                        if (gpeak > 0 && total > P.irv_ts &&
+                            __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th)
+                            r = (float)(gbest + dm.dmin);
+                        if (__float_as_uint(r) != __float_as_uint(__ldcg(d_new + p))) {
+                            __stcg(d_new + p, r);
+                            s_changed = 1;
+                        }
+                    }
+                }
+                __syncthreads();
+                rounds_total++;
+                const int ch = s_changed;
+                __syncthreads();
+                if (!ch) break;
+            }
+            // ---- commit the sweep, then erase filled pixels from the list (order preserved)
+            for (int idx = tid; idx < n; idx += RV_THREADS) {
+                const int p = list[idx];
+                const float v = __ldcg(d_new + p);
+                if (v != ADC_INVALID_F) { __stcg(d_old + p, v); lab[p] = 0; }
+            }
+            __syncthreads();
+            n_list[k] = rv_compact(n, list, [&](int, int p) { return __ldcg(d_old + p) == ADC_INVALID_F; },
+                                   [&](int i) { return list[i]; }, s_tot);
+        }
+    }
+    if (tid == 0) {
+        counters[pair * 8 + 0] = n_list[0];
+        counters[pair * 8 + 1] = n_list[1];
+        counters[pair * 8 + 2] = rounds_total;
+    }
+}
+
+void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
+    // disp_l = committed state (OLD), disp_t = working copy (NEW); both hold the post-outlier map here
+    k_region_voting<<<w.S, RV_THREADS, 0, st>>>(P, w.arms, w.disp_l, w.disp_t, w.label, w.pend, w.counters);
+    ++*launches;
+}
+
+void adc_launch_build_lists(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
+    k_build_lists<<<w.S, RV_THREADS, 0, st>>>(P.dm, w.label, w.pend, w.counters);
+    ++*launches;
+}
+
+// =============================================================================================
+// 3. Proper interpolation.  For each pixel still in a list: 16 rays (angle accumulated in double
+//    from the float quotient 3.1415926f/16), first valid disparity met along each; mismatches take
+//    the candidate whose colour is closest (first wins), occlusions the smallest disparity; no
+//    candidate -> 0.0 (the reference's value-initialised fill vector).  Results of one list are
+//    written after the whole list has been evaluated (Jacobi), the occlusion list then sees the
+//    filled mismatches -- hence one launch per list reading disp_old and writing disp_new.
+//    The ray coordinates are evaluated exactly as the reference does, lround(y + m*sin) in double
+//    without contraction, with sin/cos tables from the host's libm.
+//    16 lanes = 16 rays of one pixel; two pixels per warp.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+k_interpolate(AdcParams P, int k, const uint8_t* __restrict__ bgr, const float* __restrict__ disp_old,
+              float* __restrict__ disp_new, const int* __restrict__ pend, const int* __restrict__ counters,
+              const double* __restrict__ ray_sin, const double* __restrict__ ray_cos) {
+    const AdcDims& dm = P.dm;
+    const int pair = blockIdx.y;
+    const int n = counters[pair * 8 + k];
+    const int* list = pend + ((size_t)pair * 2 + k) * dm.N;
+    const uint8_t* left = bgr + (size_t)pair * 2 * dm.N * 3;
+    const float* d_old = disp_old + (size_t)pair * dm.N;
+    float* d_new = disp_new + (size_t)pair * dm.N;
+    const int ray = threadIdx.x & 15;
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int n_slots = (gridDim.x * blockDim.x) >> 4;
+    const unsigned half_mask = 0xffffu << (threadIdx.x & 16);
+    const double sa = ray_sin[ray], ca = ray_cos[ray];
+    for (int base = 0; base < n; base += n_slots) {   // uniform trip count for the whole warp
+        const int idx = base + slot;
+        const bool active = idx < n;
+        int p = 0, x = 0, y = 0;
+        if (active) { p = list[idx]; y = p / dm.W; x = p - y * dm.W; }
+        int dist = 0x7fffffff;
+        float dval = ADC_LARGE_F;
+        bool found = false;
+        if (active) {
+            const uchar3 c0 = adc_load_bgr(left, p);
+            for (int m = 1; m < P.max_search; m++) {
+                const long yy = lround(__dadd_rn((double)y, __dmul_rn((double)m, sa)));
+                const long xx = lround(__dadd_rn((double)x, __dmul_rn((double)m, ca)));
+                if (yy < 0 || yy >= dm.H || xx < 0 || xx >= dm.W) break;
+                const int q = (int)yy * dm.W + (int)xx;
+                const float d = d_old[q];
+                if (d != ADC_INVALID_F) {
+                    const uchar3 c = adc_load_bgr(left, q);
+                    dist = abs((int)c0.x - (int)c.x) + abs((int)c0.y - (int)c.y) + abs((int)c0.z - (int)c.z);
+                    dval = d;
+                    found = true;
+                    break;
+                }
+            }
+        }
+        // combine the 16 rays of this pixel (half-warp)
+        const unsigned any = __ballot_sync(0xffffffffu, found) & half_mask;
+        float result = 0.0f;
+        if (k == 0) {
+            // smallest colour distance, earliest ray on ties (strict '>' in the reference, min_dist starts at 9999)
+            int key = (found && dist < 9999) ? ((dist << 4) | ray) : 0x7fffffff;
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+            const int win = key & 15;
+            const float dw = __shfl_sync(0xffffffffu, dval, (threadIdx.x & 16) | win);
+            if (key != 0x7fffffff) result = dw;     // all candidates farther than 9999 keep d = 0.0f
+        } else {
+            float mv = found ? dval : ADC_LARGE_F;
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) mv = fminf(mv, __shfl_xor_sync(0xffffffffu, mv, o));
+            result = mv;
+        }
+        if (any == 0) result = 0.0f;
+        if (active && ray == 0) d_new[p] = result;
+    }
+}
+
+void adc_launch_interp_list(const AdcParams& P, const AdcWave& w, int k, cudaStream_t st, unsigned long long* launches) {
+    dim3 grid(64, w.S);
+    k_interpolate<<<grid, 256, 0, st>>>(P, k, w.bgr, w.disp_l, w.disp_t, w.pend, w.counters, w.ray_sin, w.ray_cos);
+    ++*launches;
+}
+
+// =============================================================================================
+// 4. Depth-discontinuity adjustment (default OFF in ADCensusOption).  Sobel edge mask on the
+//    disparity map, then per row a strictly sequential left-to-right pass (pixel x may copy from
+//    x-1, which may itself have just been changed) -> one thread per row.  The reference indexes
+//    the cost volume with lround(d) without subtracting dmin (multistep_refiner.cpp:331); indices
+//    outside [0,D) are undefined behaviour there and skipped here (as in oracle/adc_oracle.c).
+// =============================================================================================
+__global__ void k_edge_mask(AdcDims dm, const float* __restrict__ disp, uint8_t* __restrict__ edge) {
+    const int pair = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dm.N) return;
+    const int y = i / dm.W, x = i - y * dm.W;
+    uint8_t e = 0;
+    if (y >= 1 && y < dm.H - 1 && x >= 1 && x < dm.W - 1) {
+        const float* r1 = disp + (size_t)pair * dm.N + i;
+        const float* r0 = r1 - dm.W;
+        const float* r2 = r1 + dm.W;
+        const float A = __fadd_rn(-r0[-1], r0[1]);
+        const float B = __fadd_rn(__fmul_rn(-2.0f, r1[-1]), __fmul_rn(2.0f, r1[1]));
+        const float C = __fadd_rn(-r2[-1], r2[1]);
+        const float gx = __fadd_rn(__fadd_rn(A, B), C);
+        const float T = __fsub_rn(__fsub_rn(-r0[-1], __fmul_rn(2.0f, r0[0])), r0[1]);
+        const float U = __fadd_rn(__fadd_rn(r2[-1], __fmul_rn(2.0f, r2[0])), r2[1]);
+        const float gy = __fadd_rn(T, U);
+        if (__fadd_rn(fabsf(gx), fabsf(gy)) > 5.0f) e = 1;
+    }
+    edge[(size_t)pair * dm.N + i] = e;
+}
+
+__global__ void k_discontinuity_rows(AdcDims dm, float* __restrict__ disp, const uint8_t* __restrict__ edge,
+                                     const float* __restrict__ vol) {
+    const int pair = blockIdx.y;
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= dm.H) return;
+    float* row = disp + (size_t)pair * dm.N + (size_t)y * dm.W;
+    const uint8_t* erow = edge + (size_t)pair * dm.N + (size_t)y * dm.W;
+    for (int x = 1; x < dm.W - 1; x++) {
+        if (erow[x] != 1) continue;
+        const float d = row[x];
+        if (d == ADC_INVALID_F) continue;
+        const float* cost = vol + (size_t)pair * dm.vol_stride + ((size_t)y * dm.W + x) * dm.Dp;
+        const long di = lroundf(d);
+        if (di < 0 || di >= dm.D) continue;
+        float c0 = cost[di];
+        for (int k = 0; k < 2; k++) {
+            const float d2 = row[k == 0 ? x - 1 : x + 1];
+            if (d2 == ADC_INVALID_F) continue;
+            const long d2i = lroundf(d2);
+            if (d2i < 0 || d2i >= dm.D) continue;
+            const float cc = k == 0 ? cost[-dm.Dp + d2i] : cost[dm.Dp + d2i];
+            if (cc < c0) { row[x] = d2; c0 = cc; }
+        }
+    }
+}
+
+void adc_launch_discontinuity(const AdcParams& P, const AdcWave& w, const float* vol, cudaStream_t st, unsigned long long* launches) {
+    dim3 grid((P.dm.N + 255) / 256, w.S);
+    k_edge_mask<<<grid, 256, 0, st>>>(P.dm, w.disp_l, w.flag);
+    dim3 grid2((P.dm.H + 63) / 64, w.S);
+    k_discontinuity_rows<<<grid2, 64, 0, st>>>(P.dm, w.disp_l, w.flag, vol);
+    *launches += 2;
+}
+
+// =============================================================================================
+// 5. In-place 3x3 median in raster order.  out(y,x) sees already-filtered values in row y-1 and
+//    at (y,x-1), and original values elsewhere.  (y,x) depends on (y,x-1) and (y-1,x+1), so all
+//    pixels with x + 2y = t are independent: a wavefront over t = 0 .. W+2H-3 with a CTA barrier
+//    per step reproduces the sequential scan exactly (every window element of step t was produced
+//    at a step != t).  Window = in-image neighbours, sorted, element n/2 (9->[4], 6->[3], 4->[2]);
+//    realised as the median of 9 after padding with -inf/+inf so that the rank is preserved.
+// =============================================================================================
+#define MED_THREADS 1024
+
+__device__ __forceinline__ void cswap(float& a, float& b) { const float lo = fminf(a, b), hi = fmaxf(a, b); a = lo; b = hi; }
+
+__device__ __forceinline__ float median9(float v[9]) {
+    // 19-exchange median-of-9 selection network (Paeth / Smith)
+    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+    cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+    cswap(v[0], v[3]); cswap(v[5], v[8]); cswap(v[4], v[7]);
+    cswap(v[3], v[6]); cswap(v[1], v[4]); cswap(v[2], v[5]);
+    cswap(v[4], v[7]); cswap(v[4], v[2]); cswap(v[6], v[4]);
+    cswap(v[4], v[2]);
+    return v[4];
+}
+
+__global__ void __launch_bounds__(MED_THREADS)
+k_median_wavefront(AdcDims dm, float* __restrict__ disp) {
+    const int pair = blockIdx.x;
+    float* img = disp + (size_t)pair * dm.N;
+    const int W = dm.W, H = dm.H;
+    const float NINF = __int_as_float(0xff800000), PINF = ADC_INVALID_F;
+    const int n_steps = W + 2 * H - 2;
+    for (int t = 0; t < n_steps; t++) {
+        for (int y = threadIdx.x; y < H; y += MED_THREADS) {
+            const int x = t - 2 * y;
+            if (x < 0 || x >= W) continue;
+            float v[9];
+            int n = 0;
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                for (int dx = -1; dx <= 1; dx++) {
+                    const int yy = y + dy, xx = x + dx;
+                    const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+                    v[(dy + 1) * 3 + dx + 1] = in ? __ldcg(img + yy * W + xx) : PINF;
+                    n += in;
+                }
+            // n in {9,6,4}: wanted rank n/2 of the n real values == rank 4 of 9 after adding
+            // (4 - n/2) values of -inf and the rest +inf.  Out-of-image slots were filled with +inf;
+            // turn (4 - n/2) of them into -inf.
+            int need = 4 - n / 2;
+#pragma unroll
+            for (int j = 0; j < 9; j++) {
+                const int dy = j / 3 - 1, dx = j % 3 - 1;
+                const int yy = y + dy, xx = x + dx;
+                const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+                if (!in && need > 0) { v[j] = NINF; need--; }
+            }
+            __stcg(img + y * W + x, median9(v));
+        }
+        __syncthreads();
+    }
+}
+
+void adc_launch_median(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
+    k_median_wavefront<<<w.S, MED_THREADS, 0, st>>>(P.dm, w.disp_l);
+    ++*launches;
+}

@@ -1,0 +1,124 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, stage by stage.
+
+Bar (BASELINE.json north_star): bit-exact census / arms / support counts / WTA integer indices;
+<= 1e-4 on float costs; <= 0.01 px on sub-pixel disparity.  The kernels are built to be bit-exact
+on the float stages too, and these tests assert exact equality there as well (a failure prints the
+max abs difference so a tolerance-level deviation can be told from a real bug).
+"""
+import numpy as np
+import pytest
+
+import adc_testlib as T
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(w, h, opt, **kw):
+    import adcensus_b200 as A
+    o = A.ADCensusOption()
+    for name, _ in T.Option._fields_:
+        if not name.startswith("_"):
+            setattr(o, name, getattr(opt, name))
+    return A.Engine(w, h, o, **kw)
+
+
+def _same(name, got, want):
+    assert got.shape == want.shape, f"{name}: shape {got.shape} vs {want.shape}"
+    if got.dtype.kind == "f":
+        eq = (got.view(np.uint32) == want.view(np.uint32))
+        if not eq.all():
+            fin = np.isfinite(got) & np.isfinite(want)
+            md = float(np.abs(got[fin].astype(np.float64) - want[fin]).max()) if fin.any() else 0.0
+            inf_mismatch = int((np.isfinite(got) != np.isfinite(want)).sum())
+            raise AssertionError(f"{name}: {int((~eq).sum())} of {eq.size} values differ, max abs diff {md:.3e}, "
+                                 f"{inf_mismatch} finite/inf mismatches")
+    else:
+        assert np.array_equal(got, want), f"{name}: {int((got != want).sum())} of {got.size} values differ"
+
+
+CASES = [
+    # (W, H, D, option overrides, seed)
+    (64, 48, 16, {}, 1),
+    (97, 61, 24, {}, 2),            # odd sizes
+    (130, 70, 37, {}, 3),           # D not a multiple of 4 (padded stride)
+    (50, 40, 64, {}, 4),            # D > W: out-of-image matches everywhere
+    (9, 12, 8, {}, 5),              # W <= 9: census early return (adcensus_util.cpp:12)
+    (40, 7, 8, {}, 6),              # H <= 7
+    (80, 60, 32, {"cross_L1": 10, "cross_L2": 4, "cross_t1": 30, "cross_t2": 12, "so_tso": 25}, 7),
+    (80, 60, 32, {"do_lr_check": 0}, 8),
+    (80, 60, 32, {"do_filling": 0}, 9),
+    (80, 60, 32, {"do_discontinuity_adjustment": 1}, 10),
+    (120, 90, 48, {"lambda_ad": 7, "lambda_census": 20, "so_p1": 0.7, "so_p2": 2.5, "irv_ts": 10,
+                   "irv_th": 0.3, "lrcheck_thres": 0.5}, 11),
+    (150, 100, 130, {}, 12),        # K = 5 values per lane in the scanline kernel
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}x{c[1]}x{c[2]}-{i}" for i, c in enumerate(CASES)])
+def test_stage_parity_synthetic(case):
+    w, h, D, over, seed = case
+    opt = T.default_option(max_disparity=D, **over)
+    left, right = T.synthetic_pair(w, h, D, seed)
+    orc = T.Oracle(w, h, opt)
+    eng = _engine(w, h, opt)
+    orc.begin(left, right)
+    for st in T.STAGES:
+        orc.step()
+        eng.debug_run(left, right, st)
+        for tap in T.STAGE_TAPS[st]:
+            _same(f"{st}/{tap}", eng.tap(tap), orc.tap(tap))
+    # the public entry point gives the same map as the staged run
+    _same("match", eng.match(left, right), orc.tap("DISP_L"))
+    eng.close()
+
+
+def test_cone_all_stages(cone):
+    left, right = cone
+    h, w, _ = left.shape
+    orc = T.Oracle(w, h)
+    eng = _engine(w, h, T.default_option())
+    orc.begin(left, right)
+    for st in T.STAGES:
+        orc.step()
+        eng.debug_run(left, right, st)
+        for tap in T.STAGE_TAPS[st]:
+            _same(f"cone {st}/{tap}", eng.tap(tap), orc.tap(tap))
+    final = eng.match(left, right)
+    _same("cone match", final, orc.tap("DISP_L"))
+    eng.close()
+
+
+def test_batch_equals_single():
+    w, h, D = 96, 64, 32
+    opt = T.default_option(max_disparity=D)
+    pairs = [T.synthetic_pair(w, h, D, 100 + i) for i in range(11)]
+    lefts = np.stack([p[0] for p in pairs])
+    rights = np.stack([p[1] for p in pairs])
+    eng = _engine(w, h, opt, wave_pairs=4, lanes=2)
+    singles = [eng.match(l, r) for l, r in pairs]
+    batch = eng.match_batch(lefts, rights)
+    for i in range(len(pairs)):
+        _same(f"batch[{i}]", batch[i], singles[i])
+    ptrs = eng.match_batch_ptrs([p[0] for p in pairs], [p[1] for p in pairs])
+    for i in range(len(pairs)):
+        _same(f"ptrs[{i}]", ptrs[i], singles[i])
+    orc = T.Oracle(w, h, opt)
+    _same("vs oracle", singles[3], orc.match(*pairs[3]))
+    eng.close()
+
+
+def test_error_truth_table():
+    """Mirrors ADCensusStereo.cpp:31,38,71,74: bad sizes / empty range / null pointers -> false."""
+    import adcensus_b200 as A
+    s = A.ADCensusStereo()
+    assert s.Match(np.zeros((4, 4, 3), np.uint8), np.zeros((4, 4, 3), np.uint8)) is False  # before Initialize
+    assert s.Initialize(0, 10, A.ADCensusOption()) is False
+    assert s.Initialize(10, -1, A.ADCensusOption()) is False
+    assert s.Initialize(10, 10, A.ADCensusOption(min_disparity=5, max_disparity=5)) is False
+    assert s.Initialize(32, 24, A.ADCensusOption(max_disparity=8)) is True
+    assert s.Match(None, np.zeros((24, 32, 3), np.uint8)) is False
+    out = s.Match(np.zeros((24, 32, 3), np.uint8), np.zeros((24, 32, 3), np.uint8))
+    assert out.shape == (24, 32)
+    assert s.Reset(40, 30, A.ADCensusOption(max_disparity=16)) is True
+    assert s.Match(np.zeros((30, 40, 3), np.uint8), np.zeros((30, 40, 3), np.uint8)).shape == (30, 40)
+    s.Release()

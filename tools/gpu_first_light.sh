@@ -1,0 +1,8 @@
+#!/bin/bash
+# first GPU contact: parity tests + a rough Cone batch timing
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+cat gpurun_out/pytest_gpu.log
+timeout 600 python tools/quick_bench.py 2>&1 | tail -40 | tee gpurun_out/quick_bench.log

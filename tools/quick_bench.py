@@ -1,0 +1,37 @@
+"""Rough device-resident throughput of the Cone batch (development aid, not the contract bench)."""
+import sys, time
+from pathlib import Path
+import numpy as np
+import torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import adcensus_b200 as A
+import adc_testlib as T
+
+left, right = T.load_cone()
+h, w, _ = left.shape
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+for S, lanes in ((8, 3), (4, 3), (16, 2), (2, 4)):
+    eng = A.Engine(w, h, A.ADCensusOption(), wave_pairs=S, lanes=lanes)
+    dl = torch.from_numpy(np.repeat(left[None], n, 0)).cuda()
+    dr = torch.from_numpy(np.repeat(right[None], n, 0)).cuda()
+    dd = torch.empty((n, h, w), dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream()
+    for _ in range(2):
+        eng.match_batch_device(n, dl.data_ptr(), dr.data_ptr(), dd.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    reps = 3
+    for _ in range(reps):
+        eng.match_batch_device(n, dl.data_ptr(), dr.data_ptr(), dd.data_ptr(), st.cuda_stream)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"S={S} lanes={lanes}: {n} pairs in {ms:.2f} ms -> {n / ms * 1000:.1f} maps/s", flush=True)
+    eng.close()
+# per-stage times of a single Match
+eng = A.Engine(w, h, A.ADCensusOption())
+for _ in range(3):
+    d = eng.match(left, right)
+print("single-pair stage ms (cost, aggr, so, wta, refine, out):", [round(x, 3) for x in eng.last_stage_ms()])
