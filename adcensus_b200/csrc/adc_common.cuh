@@ -68,7 +68,10 @@ struct AdcWave {            // device pointers of one wave (S pairs)
     float* disp_l; float* disp_r; float* disp_t;
     uint8_t* label; uint8_t* flag;
     int* pend;              // [S][2][N] mismatch / occlusion pixel lists (raster order)
-    int* counters;          // [S][8]
+    int* counters;          // [S][8]: 0,1 list sizes; 2 voting rounds; 3 voting evaluations
+    int* rowcnt;            // [S][2][H] per-row list counts / offsets
+    int* tile_stamp;        // [S][tiles] region voting: epoch of the last change near a 16x16 tile
+    int* last_eval;         // [S][N]     region voting: epoch of a pixel's last evaluation
     const float* lut_ad;    // [766]  (1 - exp(-(s/3)/lambda_ad)) + 1, host libm expf
     const float* lut_cen;   // [64]   exp(-h/lambda_census)
     const double* ray_sin; const double* ray_cos; // [16] host libm sin/cos of the accumulated angles

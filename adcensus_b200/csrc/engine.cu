@@ -123,6 +123,9 @@ size_t carve_lane(void* base, const AdcDims& dm, int S, AdcWave* w) {
     t.flag = c.take<uint8_t>((size_t)S * N);
     t.pend = c.take<int>((size_t)S * 2 * N);
     t.counters = c.take<int>((size_t)S * 8);
+    t.rowcnt = c.take<int>((size_t)S * 2 * dm.H);
+    t.tile_stamp = c.take<int>((size_t)S * ((dm.W + 15) / 16) * ((dm.H + 15) / 16));
+    t.last_eval = c.take<int>((size_t)S * N);
     if (w) *w = t;
     return c.off;
 }
@@ -248,6 +251,7 @@ int enqueue_pipeline(adc_engine* e, Lane& ln, int nS, int last_stage, cudaEvent_
     }
     if (stop(ADC_STAGE_OUTLIER)) return ADC_OK;
     if (e->opt.do_filling) {  // gates voting AND interpolation (ADCensusStereo.cpp:183)
+        CK(cudaMemsetAsync(w.counters, 0, (size_t)nS * 8 * sizeof(int), st));
         adc_launch_build_lists(P, w, st, L);
         adc_launch_voting(P, w, st, L);
         if (stop(ADC_STAGE_VOTE)) return ADC_OK;

@@ -75,59 +75,135 @@ void adc_launch_outlier(const AdcParams& P, const AdcWave& w, cudaStream_t st, u
 // 2. Iterative region voting.  Reference: 5 iterations x {mismatch list, occlusion list}; within a
 //    sweep pixels are visited in list (= raster) order and a filled pixel is immediately visible to
 //    later ones (Gauss-Seidel).  Exact parallel form ("raster-aware fixed point"): keep OLD (state at
-//    sweep start) and NEW.  Repeatedly recompute every pending pixel p of the list in parallel,
-//    reading neighbour q from NEW if q precedes p in raster order and from OLD otherwise, until a
-//    full round changes nothing.  The sequential result is the unique fixed point of that map (by
-//    induction over raster order: the first pending pixel only depends on OLD, pixel p only on OLD
-//    and on earlier pixels), so ANY asynchronous evaluation order converges to it; a round that
-//    changes nothing was computed entirely from settled values and therefore certifies it.
-//    One CTA per stereo pair; the batch supplies the parallelism across SMs.
+//    sweep start) and NEW.  Repeatedly recompute pending pixels p of the list in parallel, reading
+//    neighbour q from NEW if q precedes p in raster order and from OLD otherwise, until a full round
+//    changes nothing.  The sequential result is the unique fixed point of that map (induction over
+//    raster order: the first pending pixel only depends on OLD, pixel p only on OLD and on earlier
+//    pixels), so ANY asynchronous evaluation order converges to it, and a round without changes
+//    certifies it.
+//    Work filter (does not change the fixed point): a pixel's vote is a pure function of the
+//    disparities inside its cross region, which lies within +-L1 of it.  Every value change stamps
+//    the 16x16 tiles within that reach with the current epoch; a pending pixel is re-evaluated only
+//    if its tile carries a stamp >= the epoch of its own last evaluation.  Otherwise its inputs are
+//    bit-for-bit what they were and so is its vote -- this also carries over from sweep to sweep.
+//    One CTA per stereo pair (so plain L1-cached accesses are coherent); the batch and the other
+//    lanes keep the rest of the chip busy.
 // =============================================================================================
 #define RV_THREADS 1024
 #define RV_WARPS (RV_THREADS / 32)
 #define RV_MAXD 256
+#define RV_TILE 16
 
-// ordered compaction of `n_in` candidates (keep[i] decided by the caller's lambda) -- helper
-template <typename KeepFn, typename ValFn>
-__device__ int rv_compact(int n_in, int* __restrict__ out, KeepFn keep, ValFn val, int* s_warp_tot) {
+// ---- ordered (raster) pixel lists of the two outlier classes: row counts -> scan -> scatter ----
+__global__ void __launch_bounds__(128)
+k_list_row_counts(AdcDims dm, const uint8_t* __restrict__ label, int* __restrict__ rowcnt) {
+    const int pair = blockIdx.y, y = blockIdx.x;
+    const uint8_t* lab = label + (size_t)pair * dm.N + (size_t)y * dm.W;
+    int c1 = 0, c2 = 0;
+    for (int x = threadIdx.x; x < dm.W; x += 128) { const uint8_t v = lab[x]; c1 += v == 1; c2 += v == 2; }
+    __shared__ int s1[4], s2[4];
+    c1 = __reduce_add_sync(0xffffffffu, c1);
+    c2 = __reduce_add_sync(0xffffffffu, c2);
+    if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = c1; s2[threadIdx.x >> 5] = c2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        rowcnt[((size_t)pair * 2 + 0) * dm.H + y] = s1[0] + s1[1] + s1[2] + s1[3];
+        rowcnt[((size_t)pair * 2 + 1) * dm.H + y] = s2[0] + s2[1] + s2[2] + s2[3];
+    }
+}
+
+// exclusive scan of the row counts (in place), one warp per (pair, class)
+__global__ void __launch_bounds__(64)
+k_list_row_scan(AdcDims dm, int* __restrict__ rowcnt, int* __restrict__ counters) {
+    const int pair = blockIdx.x, k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* rc = rowcnt + ((size_t)pair * 2 + k) * dm.H;
+    int base = 0;
+    for (int y0 = 0; y0 < dm.H; y0 += 32) {
+        const int y = y0 + lane;
+        const int v = y < dm.H ? rc[y] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (y < dm.H) rc[y] = base + inc - v;
+        base += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) counters[pair * 8 + k] = base;
+}
+
+__global__ void __launch_bounds__(128)
+k_list_row_scatter(AdcDims dm, const uint8_t* __restrict__ label, const int* __restrict__ rowoff, int* __restrict__ pend) {
+    const int pair = blockIdx.y, y = blockIdx.x;
+    const uint8_t* lab = label + (size_t)pair * dm.N + (size_t)y * dm.W;
+    __shared__ int s_cnt[2][4];
+    int base1 = rowoff[((size_t)pair * 2 + 0) * dm.H + y], base2 = rowoff[((size_t)pair * 2 + 1) * dm.H + y];
+    int* l1 = pend + ((size_t)pair * 2 + 0) * dm.N;
+    int* l2 = pend + ((size_t)pair * 2 + 1) * dm.N;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int x0 = 0; x0 < dm.W; x0 += 128) {
+        const int x = x0 + threadIdx.x;
+        const uint8_t v = x < dm.W ? lab[x] : 0;
+        const unsigned b1 = __ballot_sync(0xffffffffu, v == 1), b2 = __ballot_sync(0xffffffffu, v == 2);
+        if (lane == 0) { s_cnt[0][wid] = __popc(b1); s_cnt[1][wid] = __popc(b2); }
+        __syncthreads();
+        int o1 = base1, o2 = base2, t1 = 0, t2 = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < 4; w2++) {
+            if (w2 < wid) { o1 += s_cnt[0][w2]; o2 += s_cnt[1][w2]; }
+            t1 += s_cnt[0][w2]; t2 += s_cnt[1][w2];
+        }
+        const unsigned lt = (1u << lane) - 1u;
+        if (v == 1) l1[o1 + __popc(b1 & lt)] = y * dm.W + x;
+        if (v == 2) l2[o2 + __popc(b2 & lt)] = y * dm.W + x;
+        base1 += t1; base2 += t2;
+        __syncthreads();
+    }
+}
+
+void adc_launch_build_lists(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
+    dim3 grid(P.dm.H, w.S);
+    k_list_row_counts<<<grid, 128, 0, st>>>(P.dm, w.label, w.rowcnt);
+    k_list_row_scan<<<w.S, 64, 0, st>>>(P.dm, w.rowcnt, w.counters);
+    k_list_row_scatter<<<grid, 128, 0, st>>>(P.dm, w.label, w.rowcnt, w.pend);
+    *launches += 3;
+}
+
+// in-place ordered compaction of list[0..n) keeping the pixels that are still invalid
+__device__ int rv_compact_invalid(int n, int* __restrict__ list, const float* __restrict__ d_old, int* s_warp_tot) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     int base = 0;
-    for (int start = 0; start < n_in; start += RV_THREADS) {
+    for (int start = 0; start < n; start += RV_THREADS) {
         const int i = start + tid;
-        int v = 0;
-        bool k = false;
-        if (i < n_in) { v = val(i); k = keep(i, v); }
-        const unsigned b = __ballot_sync(0xffffffffu, k);
+        int p = 0;
+        bool keep = false;
+        if (i < n) { p = list[i]; keep = d_old[p] == ADC_INVALID_F; }
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_warp_tot[wid] = __popc(b);
-        __syncthreads();  // also orders this chunk's reads before its writes (in-place compaction)
+        __syncthreads();  // also orders this chunk's reads before its writes
         int off = base, tot = 0;
         for (int w2 = 0; w2 < RV_WARPS; w2++) {
             const int c = s_warp_tot[w2];
             if (w2 < wid) off += c;
             tot += c;
         }
-        if (k) out[off + __popc(b & ((1u << lane) - 1u))] = v;
+        if (keep) list[off + __popc(b & ((1u << lane) - 1u))] = p;
         base += tot;
         __syncthreads();
     }
     return base;
 }
 
-__global__ void __launch_bounds__(RV_THREADS)
-k_build_lists(AdcDims dm, const uint8_t* __restrict__ label, int* __restrict__ pend, int* __restrict__ counters) {
-    __shared__ int s_tot[RV_WARPS];
-    const int pair = blockIdx.x;
-    const uint8_t* lab = label + (size_t)pair * dm.N;
-    for (int k = 0; k < 2; k++) {
-        int* list = pend + ((size_t)pair * 2 + k) * dm.N;
-        const int n = rv_compact(dm.N, list, [&](int i, int) { return lab[i] == k + 1; }, [&](int i) { return i; }, s_tot);
-        if (threadIdx.x == 0) counters[pair * 8 + k] = n;
-    }
+__device__ __forceinline__ void rv_stamp_tiles(int* __restrict__ tiles, int tw, int th, int x, int y, int reach,
+                                               int epoch, int lane) {
+    const int tx0 = max(0, (x - reach) / RV_TILE), tx1 = min(tw - 1, (x + reach) / RV_TILE);
+    const int ty0 = max(0, (y - reach) / RV_TILE), ty1 = min(th - 1, (y + reach) / RV_TILE);
+    const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
+    for (int i = lane; i < nt; i += 32) tiles[(ty0 + i / nx) * tw + tx0 + i % nx] = epoch;
 }
 
 __global__ void __launch_bounds__(RV_THREADS)
 k_region_voting(AdcParams P, const uchar4* __restrict__ arms, float* disp_old, float* disp_new,
-                uint8_t* __restrict__ label, int* __restrict__ pend, int* __restrict__ counters) {
+                uint8_t* __restrict__ label, int* __restrict__ pend, int* __restrict__ counters,
+                int* __restrict__ tile_stamp, int* __restrict__ last_eval) {
     __shared__ int s_hist[RV_WARPS][RV_MAXD];
     __shared__ int s_tot[RV_WARPS];
     __shared__ int s_changed;
@@ -135,38 +211,53 @@ k_region_voting(AdcParams P, const uchar4* __restrict__ arms, float* disp_old, f
     const int pair = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int W = dm.W, D = dm.D;
+    const int tw = (W + RV_TILE - 1) / RV_TILE, th = (dm.H + RV_TILE - 1) / RV_TILE;
+    const int reach = max(P.L1, 0);
     const uchar4* A = arms + (size_t)pair * dm.N;
     float* d_old = disp_old + (size_t)pair * dm.N;
     float* d_new = disp_new + (size_t)pair * dm.N;
     uint8_t* lab = label + (size_t)pair * dm.N;
+    int* tiles = tile_stamp + (size_t)pair * tw * th;
+    int* evalep = last_eval + (size_t)pair * dm.N;
     int n_list[2] = {counters[pair * 8 + 0], counters[pair * 8 + 1]};
-    int rounds_total = 0;
+    int rounds_total = 0, evals = 0;
     int* hist = s_hist[wid];
     const int grp = lane >> 3, sub = lane & 7;
+
+    // nothing stamped, nothing evaluated: stamp(0) >= last_eval(0) makes the first round evaluate everyone
+    for (int i = tid; i < tw * th; i += RV_THREADS) tiles[i] = 0;
+    for (int k = 0; k < 2; k++) {
+        const int* list = pend + ((size_t)pair * 2 + k) * dm.N;
+        for (int i = tid; i < n_list[k]; i += RV_THREADS) evalep[list[i]] = 0;
+    }
+    int epoch = 1;
+    __syncthreads();
 
     for (int it = 0; it < 5; it++) {
         for (int k = 0; k < 2; k++) {
             int* list = pend + ((size_t)pair * 2 + k) * dm.N;
             const int n = n_list[k];
             if (n == 0) continue;  // uniform across the CTA
-            // ---- rounds until a full pass changes nothing
+            bool any_fill = false;
             while (true) {
                 if (tid == 0) s_changed = 0;
                 __syncthreads();
                 for (int idx = wid; idx < n; idx += RV_WARPS) {
                     const int p = list[idx];
                     const int y = p / W, x = p - y * W;
+                    if (tiles[(y / RV_TILE) * tw + x / RV_TILE] < evalep[p]) continue;  // inputs untouched since
+                    evals++;
                     for (int b = lane; b < D; b += 32) hist[b] = 0;
                     __syncwarp();
-                    const uchar4 a = __ldg(A + p);
+                    const uchar4 a = A[p];
                     for (int t = -(int)a.z + grp; t <= (int)a.w; t += 4) {
                         const int rowi = (y + t) * W + x;
-                        const uchar4 a2 = __ldg(A + rowi);
+                        const uchar4 a2 = A[rowi];
                         for (int s = -(int)a2.x + sub; s <= (int)a2.y; s += 8) {
                             const bool before = (t < 0) || (t == 0 && s < 0);
-                            const float d = before ? __ldcg(d_new + rowi + s) : __ldcg(d_old + rowi + s);
+                            const float d = before ? d_new[rowi + s] : d_old[rowi + s];
                             if (d != ADC_INVALID_F) {
-                                const long di = lroundf(d) - dm.dmin;
+                                const int di = (int)roundf(d) - dm.dmin;  // lround: half away from zero
                                 if (di >= 0 && di < D) atomicAdd(&hist[di], 1);
                             }
                         }
@@ -181,35 +272,45 @@ k_region_voting(AdcParams P, const uchar4* __restrict__ arms, float* disp_old, f
                     const int gpeak = __reduce_max_sync(0xffffffffu, peak);
                     const int gbest = __reduce_min_sync(0xffffffffu, peak == gpeak ? best : 0x7fffffff);
                     total = __reduce_add_sync(0xffffffffu, total);
+                    float r = ADC_INVALID_F;
+                    if (gpeak > 0 && total > P.irv_ts &&
+                        __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th)
+                        r = (float)(gbest + dm.dmin);
+                    const bool changed = __float_as_uint(r) != __float_as_uint(d_new[p]);
                     __syncwarp();
                     if (lane == 0) {
-                        float r = ADC_INVALID_F;
-                        if (gpeak > 0 && total > P.irv_ts &&
-                            __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th)
-                            r = (float)(gbest + dm.dmin);
-                        if (__float_as_uint(r) != __float_as_uint(__ldcg(d_new + p))) {
-                            __stcg(d_new + p, r);
-                            s_changed = 1;
-                        }
+                        evalep[p] = epoch;
+                        if (changed) { d_new[p] = r; s_changed = 1; }
                     }
+                    if (changed) rv_stamp_tiles(tiles, tw, th, x, y, reach, epoch, lane);
                 }
                 __syncthreads();
                 rounds_total++;
+                epoch++;
                 const int ch = s_changed;
                 __syncthreads();
                 if (!ch) break;
+                any_fill = true;
             }
-            // ---- commit the sweep, then erase filled pixels from the list (order preserved)
-            for (int idx = tid; idx < n; idx += RV_THREADS) {
+            if (!any_fill) continue;  // nothing was filled in this sweep: list and maps unchanged
+            // ---- commit the sweep (OLD <- NEW for filled pixels; they become visible to everyone, so
+            //      their neighbourhoods are stamped again), then erase them from the list
+            for (int idx = wid; idx < n; idx += RV_WARPS) {
                 const int p = list[idx];
-                const float v = __ldcg(d_new + p);
-                if (v != ADC_INVALID_F) { __stcg(d_old + p, v); lab[p] = 0; }
+                const float v = d_new[p];
+                if (v != ADC_INVALID_F) {
+                    if (lane == 0) { d_old[p] = v; lab[p] = 0; }
+                    const int y = p / W;
+                    rv_stamp_tiles(tiles, tw, th, p - y * W, y, reach, epoch, lane);
+                }
             }
+            epoch++;
             __syncthreads();
-            n_list[k] = rv_compact(n, list, [&](int, int p) { return __ldcg(d_old + p) == ADC_INVALID_F; },
-                                   [&](int i) { return list[i]; }, s_tot);
+            n_list[k] = rv_compact_invalid(n, list, d_old, s_tot);
         }
     }
+    evals = __reduce_add_sync(0xffffffffu, lane == 0 ? evals : 0);
+    if (lane == 0) atomicAdd(&counters[pair * 8 + 3], evals);
     if (tid == 0) {
         counters[pair * 8 + 0] = n_list[0];
         counters[pair * 8 + 1] = n_list[1];
@@ -219,12 +320,8 @@ k_region_voting(AdcParams P, const uchar4* __restrict__ arms, float* disp_old, f
 
 void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
     // disp_l = committed state (OLD), disp_t = working copy (NEW); both hold the post-outlier map here
-    k_region_voting<<<w.S, RV_THREADS, 0, st>>>(P, w.arms, w.disp_l, w.disp_t, w.label, w.pend, w.counters);
-    ++*launches;
-}
-
-void adc_launch_build_lists(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
-    k_build_lists<<<w.S, RV_THREADS, 0, st>>>(P.dm, w.label, w.pend, w.counters);
+    k_region_voting<<<w.S, RV_THREADS, 0, st>>>(P, w.arms, w.disp_l, w.disp_t, w.label, w.pend, w.counters,
+                                                w.tile_stamp, w.last_eval);
     ++*launches;
 }
 
@@ -303,7 +400,7 @@ k_interpolate(AdcParams P, int k, const uint8_t* __restrict__ bgr, const float* 
 }
 
 void adc_launch_interp_list(const AdcParams& P, const AdcWave& w, int k, cudaStream_t st, unsigned long long* launches) {
-    dim3 grid(64, w.S);
+    dim3 grid(148, w.S);
     k_interpolate<<<grid, 256, 0, st>>>(P, k, w.bgr, w.disp_l, w.disp_t, w.pend, w.counters, w.ray_sin, w.ray_cos);
     ++*launches;
 }
@@ -396,7 +493,7 @@ __device__ __forceinline__ float median9(float v[9]) {
 }
 
 __global__ void __launch_bounds__(MED_THREADS)
-k_median_wavefront(AdcDims dm, float* __restrict__ disp) {
+k_median_wavefront(AdcDims dm, float* disp) {
     const int pair = blockIdx.x;
     float* img = disp + (size_t)pair * dm.N;
     const int W = dm.W, H = dm.H;
@@ -414,7 +511,7 @@ k_median_wavefront(AdcDims dm, float* __restrict__ disp) {
                 for (int dx = -1; dx <= 1; dx++) {
                     const int yy = y + dy, xx = x + dx;
                     const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
-                    v[(dy + 1) * 3 + dx + 1] = in ? __ldcg(img + yy * W + xx) : PINF;
+                    v[(dy + 1) * 3 + dx + 1] = in ? img[yy * W + xx] : PINF;
                     n += in;
                 }
             // n in {9,6,4}: wanted rank n/2 of the n real values == rank 4 of 9 after adding
@@ -428,7 +525,7 @@ k_median_wavefront(AdcDims dm, float* __restrict__ disp) {
                 const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
                 if (!in && need > 0) { v[j] = NINF; need--; }
             }
-            __stcg(img + y * W + x, median9(v));
+            img[y * W + x] = median9(v);
         }
         __syncthreads();
     }
