@@ -70,6 +70,8 @@ struct AdcWave {            // device pointers of one wave (S pairs)
     int* pend;              // [S][2][N] mismatch / occlusion pixel lists (raster order)
     int* counters;          // [S][8]: 0,1 list sizes; 2 voting rounds; 3 voting evaluations
     int* rowcnt;            // [S][2][H] per-row list counts / offsets
+    unsigned* so_bitrows;   // [S][4][H][row words] mirrored per-row bit vectors of the right image (scanline optimiser)
+    unsigned* so_rec;       // [S][N][rec words] per-pixel penalty records of the pass being run
     int* tile_stamp;        // [S][tiles] region voting: epoch of the last change near a 16x16 tile
     int* last_eval;         // [S][N]     region voting: epoch of a pixel's last evaluation
     const float* lut_ad;    // [766]  (1 - exp(-(s/3)/lambda_ad)) + 1, host libm expf
@@ -85,6 +87,9 @@ void adc_launch_arms(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsi
 // optionally divided by the support count `sup` (second pass of an iteration)
 void adc_launch_arm_sum(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int dir,
                         const uint16_t* sup, cudaStream_t st, unsigned long long* launches);
+void adc_launch_so_bitrows(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
+size_t adc_so_rec_bytes(const AdcDims& dm);
+size_t adc_so_bitrow_bytes(const AdcDims& dm);
 // one scanline pass: (sx,sy) in {(1,0),(-1,0),(0,1),(0,-1)}
 int adc_launch_scanline(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
                         cudaStream_t st, unsigned long long* launches);

@@ -124,6 +124,8 @@ size_t carve_lane(void* base, const AdcDims& dm, int S, AdcWave* w) {
     t.pend = c.take<int>((size_t)S * 2 * N);
     t.counters = c.take<int>((size_t)S * 8);
     t.rowcnt = c.take<int>((size_t)S * 2 * dm.H);
+    t.so_bitrows = c.take<unsigned>((size_t)S * adc_so_bitrow_bytes(dm) / 4);
+    t.so_rec = c.take<unsigned>((size_t)S * adc_so_rec_bytes(dm) / 4);
     t.tile_stamp = c.take<int>((size_t)S * ((dm.W + 15) / 16) * ((dm.H + 15) / 16));
     t.last_eval = c.take<int>((size_t)S * N);
     if (w) *w = t;
@@ -225,6 +227,7 @@ int enqueue_pipeline(adc_engine* e, Lane& ln, int nS, int last_stage, cudaEvent_
 
     // ---- stage 3: scanline optimisation, 4 chained passes (scanline_optimizer.cpp:54-60)
     adc_launch_diffmaps(P, w, st, L);
+    adc_launch_so_bitrows(P, w, st, L);
     static const int dirs[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
     for (int ps = 0; ps < 4; ps++) {
         const float* src = (ps % 2 == 0) ? A : B;
@@ -426,9 +429,9 @@ int adc_create(int32_t width, int32_t height, const adc_option* opt, const adc_c
     auto bail = [&](int rc) { adc_destroy(e); return rc; };
     if (cudaSetDevice(e->cfg.device) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "cudaSetDevice failed"));
 
-    // wave size: enough scanlines in flight for the warp-per-line scanline kernels (~3k lines)
+    // wave size: enough scanlines in flight for the warp-per-line scanline kernels (~6k lines = 40 warps/SM)
     int S = e->cfg.wave_pairs;
-    if (S <= 0) S = std::min(16, std::max(2, (3072 + std::min(width, height) - 1) / std::min(width, height)));
+    if (S <= 0) S = std::min(32, std::max(2, (6144 + std::min(width, height) - 1) / std::min(width, height)));
     int nl = e->cfg.lanes > 0 ? e->cfg.lanes : 3;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "cudaMemGetInfo failed"));
@@ -583,6 +586,13 @@ int adc_debug_run(adc_engine* e, const uint8_t* img_left, const uint8_t* img_rig
     if (rc) return rc;
     CK(cudaStreamSynchronize(ln.st));
     CK(cudaGetLastError());
+    return ADC_OK;
+}
+
+int adc_debug_counters(adc_engine* e, int32_t out[8]) {
+    if (!e || !out) return fail(ADC_ERR_ARG, "adc_debug_counters: bad arguments");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpy(out, e->lanes[0].w.counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return ADC_OK;
 }
 

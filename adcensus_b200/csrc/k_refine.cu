@@ -8,6 +8,12 @@
 // result (argument given at each kernel); none of them approximates.
 #include "adc_common.cuh"
 
+// barrier over all threads of the thread-block cluster, with release/acquire ordering of memory
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
 // =============================================================================================
 // 1. Outlier detection.  The raster scan reads disp_left[col_rl] of the same row while already
 //    having invalidated pixels to the left of x.  Whether a pixel gets invalidated depends only on
@@ -167,15 +173,15 @@ void adc_launch_build_lists(const AdcParams& P, const AdcWave& w, cudaStream_t s
     *launches += 3;
 }
 
-// in-place ordered compaction of list[0..n) keeping the pixels that are still invalid
-__device__ int rv_compact_invalid(int n, int* __restrict__ list, const float* __restrict__ d_old, int* s_warp_tot) {
+// in-place ordered compaction of list[0..n) keeping the pixels that are still invalid (one CTA)
+__device__ int rv_compact_invalid(int n, int* list, const float* d_old, int* s_warp_tot) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     int base = 0;
     for (int start = 0; start < n; start += RV_THREADS) {
         const int i = start + tid;
         int p = 0;
         bool keep = false;
-        if (i < n) { p = list[i]; keep = d_old[p] == ADC_INVALID_F; }
+        if (i < n) { p = __ldcg(list + i); keep = __ldcg(d_old + p) == ADC_INVALID_F; }
         const unsigned b = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_warp_tot[wid] = __popc(b);
         __syncthreads();  // also orders this chunk's reads before its writes
@@ -185,31 +191,37 @@ __device__ int rv_compact_invalid(int n, int* __restrict__ list, const float* __
             if (w2 < wid) off += c;
             tot += c;
         }
-        if (keep) list[off + __popc(b & ((1u << lane) - 1u))] = p;
+        if (keep) __stcg(list + off + __popc(b & ((1u << lane) - 1u)), p);
         base += tot;
         __syncthreads();
     }
     return base;
 }
 
-__device__ __forceinline__ void rv_stamp_tiles(int* __restrict__ tiles, int tw, int th, int x, int y, int reach,
-                                               int epoch, int lane) {
+__device__ __forceinline__ void rv_stamp_tiles(int* tiles, int tw, int th, int x, int y, int reach, int epoch, int lane) {
     const int tx0 = max(0, (x - reach) / RV_TILE), tx1 = min(tw - 1, (x + reach) / RV_TILE);
     const int ty0 = max(0, (y - reach) / RV_TILE), ty1 = min(th - 1, (y + reach) / RV_TILE);
     const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
-    for (int i = lane; i < nt; i += 32) tiles[(ty0 + i / nx) * tw + tx0 + i % nx] = epoch;
+    for (int i = lane; i < nt; i += 32) __stcg(tiles + (ty0 + i / nx) * tw + tx0 + i % nx, epoch);
 }
 
-__global__ void __launch_bounds__(RV_THREADS)
+// A thread-block cluster of RV_CLUSTER CTAs works on one stereo pair: the pending pixels of a
+// round are dealt round-robin to its RV_CLUSTER*32 warps, the rounds are separated by cluster
+// barriers, and all mutable state lives in global memory and is accessed at L2 (ld.cg / st.cg)
+// because the CTAs sit on different SMs.
+#define RV_CLUSTER 8
+
+__global__ void __cluster_dims__(RV_CLUSTER, 1, 1) __launch_bounds__(RV_THREADS)
 k_region_voting(AdcParams P, const uchar4* __restrict__ arms, float* disp_old, float* disp_new,
-                uint8_t* __restrict__ label, int* __restrict__ pend, int* __restrict__ counters,
-                int* __restrict__ tile_stamp, int* __restrict__ last_eval) {
+                uint8_t* label, int* pend, int* counters, int* tile_stamp, int* last_eval) {
     __shared__ int s_hist[RV_WARPS][RV_MAXD];
     __shared__ int s_tot[RV_WARPS];
-    __shared__ int s_changed;
     const AdcDims& dm = P.dm;
-    const int pair = blockIdx.x;
+    const int pair = blockIdx.x / RV_CLUSTER;
+    const int crank = blockIdx.x % RV_CLUSTER;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int gwarp = crank * RV_WARPS + wid, n_gwarps = RV_CLUSTER * RV_WARPS;
+    const int gtid = crank * RV_THREADS + tid, n_gthreads = RV_CLUSTER * RV_THREADS;
     const int W = dm.W, D = dm.D;
     const int tw = (W + RV_TILE - 1) / RV_TILE, th = (dm.H + RV_TILE - 1) / RV_TILE;
     const int reach = max(P.L1, 0);
@@ -219,43 +231,45 @@ k_region_voting(AdcParams P, const uchar4* __restrict__ arms, float* disp_old, f
     uint8_t* lab = label + (size_t)pair * dm.N;
     int* tiles = tile_stamp + (size_t)pair * tw * th;
     int* evalep = last_eval + (size_t)pair * dm.N;
-    int n_list[2] = {counters[pair * 8 + 0], counters[pair * 8 + 1]};
+    int* cnt = counters + pair * 8;   // 0,1: list sizes   2: rounds   3: evaluations   4..6: change flags (mod 3)
+    int n_list[2] = {__ldcg(cnt + 0), __ldcg(cnt + 1)};
     int rounds_total = 0, evals = 0;
     int* hist = s_hist[wid];
     const int grp = lane >> 3, sub = lane & 7;
 
     // nothing stamped, nothing evaluated: stamp(0) >= last_eval(0) makes the first round evaluate everyone
-    for (int i = tid; i < tw * th; i += RV_THREADS) tiles[i] = 0;
+    for (int i = gtid; i < tw * th; i += n_gthreads) __stcg(tiles + i, 0);
     for (int k = 0; k < 2; k++) {
         const int* list = pend + ((size_t)pair * 2 + k) * dm.N;
-        for (int i = tid; i < n_list[k]; i += RV_THREADS) evalep[list[i]] = 0;
+        for (int i = gtid; i < n_list[k]; i += n_gthreads) __stcg(evalep + list[i], 0);
     }
-    int epoch = 1;
-    __syncthreads();
+    if (gtid < 3) __stcg(cnt + 4 + gtid, 0);
+    int epoch = 1, rnd = 0;   // rnd indexes the three rotating change flags
+    cluster_sync_all();
 
     for (int it = 0; it < 5; it++) {
         for (int k = 0; k < 2; k++) {
             int* list = pend + ((size_t)pair * 2 + k) * dm.N;
             const int n = n_list[k];
-            if (n == 0) continue;  // uniform across the CTA
+            if (n == 0) continue;  // uniform across the cluster
             bool any_fill = false;
             while (true) {
-                if (tid == 0) s_changed = 0;
-                __syncthreads();
-                for (int idx = wid; idx < n; idx += RV_WARPS) {
-                    const int p = list[idx];
+                if (gtid == 0) __stcg(cnt + 4 + (rnd + 1) % 3, 0);  // flag of the NEXT round; nobody reads it now
+                bool warp_changed = false;
+                for (int idx = gwarp; idx < n; idx += n_gwarps) {
+                    const int p = __ldcg(list + idx);
                     const int y = p / W, x = p - y * W;
-                    if (tiles[(y / RV_TILE) * tw + x / RV_TILE] < evalep[p]) continue;  // inputs untouched since
+                    if (__ldcg(tiles + (y / RV_TILE) * tw + x / RV_TILE) < __ldcg(evalep + p)) continue;  // inputs untouched since
                     evals++;
                     for (int b = lane; b < D; b += 32) hist[b] = 0;
                     __syncwarp();
-                    const uchar4 a = A[p];
+                    const uchar4 a = __ldg(A + p);
                     for (int t = -(int)a.z + grp; t <= (int)a.w; t += 4) {
                         const int rowi = (y + t) * W + x;
-                        const uchar4 a2 = A[rowi];
+                        const uchar4 a2 = __ldg(A + rowi);
                         for (int s = -(int)a2.x + sub; s <= (int)a2.y; s += 8) {
                             const bool before = (t < 0) || (t == 0 && s < 0);
-                            const float d = before ? d_new[rowi + s] : d_old[rowi + s];
+                            const float d = before ? __ldcg(d_new + rowi + s) : __ldcg(d_old + rowi + s);
                             if (d != ADC_INVALID_F) {
                                 const int di = (int)roundf(d) - dm.dmin;  // lround: half away from zero
                                 if (di >= 0 && di < D) atomicAdd(&hist[di], 1);
@@ -276,52 +290,54 @@ k_region_voting(AdcParams P, const uchar4* __restrict__ arms, float* disp_old, f
                     if (gpeak > 0 && total > P.irv_ts &&
                         __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th)
                         r = (float)(gbest + dm.dmin);
-                    const bool changed = __float_as_uint(r) != __float_as_uint(d_new[p]);
+                    const bool changed = __float_as_uint(r) != __float_as_uint(__ldcg(d_new + p));
                     __syncwarp();
                     if (lane == 0) {
-                        evalep[p] = epoch;
-                        if (changed) { d_new[p] = r; s_changed = 1; }
+                        __stcg(evalep + p, epoch);
+                        if (changed) __stcg(d_new + p, r);
                     }
-                    if (changed) rv_stamp_tiles(tiles, tw, th, x, y, reach, epoch, lane);
+                    if (changed) { rv_stamp_tiles(tiles, tw, th, x, y, reach, epoch, lane); warp_changed = true; }
                 }
-                __syncthreads();
+                if (warp_changed && lane == 0) __stcg(cnt + 4 + rnd % 3, 1);
+                cluster_sync_all();
+                const int ch = __ldcg(cnt + 4 + rnd % 3);
                 rounds_total++;
                 epoch++;
-                const int ch = s_changed;
-                __syncthreads();
+                rnd++;
                 if (!ch) break;
                 any_fill = true;
             }
             if (!any_fill) continue;  // nothing was filled in this sweep: list and maps unchanged
             // ---- commit the sweep (OLD <- NEW for filled pixels; they become visible to everyone, so
             //      their neighbourhoods are stamped again), then erase them from the list
-            for (int idx = wid; idx < n; idx += RV_WARPS) {
-                const int p = list[idx];
-                const float v = d_new[p];
+            for (int idx = gwarp; idx < n; idx += n_gwarps) {
+                const int p = __ldcg(list + idx);
+                const float v = __ldcg(d_new + p);
                 if (v != ADC_INVALID_F) {
-                    if (lane == 0) { d_old[p] = v; lab[p] = 0; }
+                    if (lane == 0) { __stcg(d_old + p, v); lab[p] = 0; }
                     const int y = p / W;
                     rv_stamp_tiles(tiles, tw, th, p - y * W, y, reach, epoch, lane);
                 }
             }
             epoch++;
-            __syncthreads();
-            n_list[k] = rv_compact_invalid(n, list, d_old, s_tot);
+            cluster_sync_all();
+            if (crank == 0) {
+                const int kept = rv_compact_invalid(n, list, d_old, s_tot);
+                if (tid == 0) __stcg(cnt + k, kept);
+            }
+            cluster_sync_all();
+            n_list[k] = __ldcg(cnt + k);
         }
     }
     evals = __reduce_add_sync(0xffffffffu, lane == 0 ? evals : 0);
-    if (lane == 0) atomicAdd(&counters[pair * 8 + 3], evals);
-    if (tid == 0) {
-        counters[pair * 8 + 0] = n_list[0];
-        counters[pair * 8 + 1] = n_list[1];
-        counters[pair * 8 + 2] = rounds_total;
-    }
+    if (lane == 0) atomicAdd(cnt + 3, evals);
+    if (gtid == 0) __stcg(cnt + 2, rounds_total);
 }
 
 void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
     // disp_l = committed state (OLD), disp_t = working copy (NEW); both hold the post-outlier map here
-    k_region_voting<<<w.S, RV_THREADS, 0, st>>>(P, w.arms, w.disp_l, w.disp_t, w.label, w.pend, w.counters,
-                                                w.tile_stamp, w.last_eval);
+    k_region_voting<<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.disp_l, w.disp_t, w.label, w.pend, w.counters,
+                                                             w.tile_stamp, w.last_eval);
     ++*launches;
 }
 

@@ -10,27 +10,36 @@
 // cross lanes through two shuffles; the minimum over d is one REDUX on order-preserving integer
 // keys.  Only add/min/exact scalings occur, so the result is bit-identical to the CPU path.
 //
-// P1/P2 depend on d1 = Dc(left[p], left[p_prev]) and d2 = Dc(right[xr], right[xr_prev]) with
-// xr = x - d - dmin.  The reference declares d2 once per pixel (initialised to d1) and only
-// overwrites it while 0 < xr < W-1, so for disparities past the valid interval it keeps the value of
-// the last valid one ("sticky d2", :116-121).  Closed form used here: valid d form the interval
-// [lo,hi] = [max(0,x-dmin-(W-2)), min(D-1,x-dmin-1)]; d<lo -> d1, d in [lo,hi] -> map(x-d-dmin),
-// d>hi -> map(x-hi-dmin), empty interval -> d1.
+// Memory system: everything a step needs that does not depend on the recurrence -- the pixel's
+// cost vector (Dp floats) and a small "penalty record" -- is streamed into a per-warp shared
+// memory ring with cp.async (LDGSTS), SO_PF steps ahead, so HBM/L2 latency never sits on the
+// serial chain and the number of bytes in flight per SM is set by the ring depth, not by
+// register scoreboards.
+//
+// Penalty record.  P1/P2 depend on d1 = Dc(left[p], left[p_prev]) and d2 = Dc(right[xr],
+// right[xr_prev]) with xr = x - d - dmin, through (d1 < tso, d2 < tso).  The reference declares d2
+// once per pixel (initialised to d1) and only overwrites it while 0 < xr < W-1, so for
+// disparities past the valid interval it keeps the value of the last valid one ("sticky d2",
+// :116-121).  Closed form: valid d form [lo,hi] = [max(0,x-dmin-(W-2)), min(D-1,x-dmin-1)];
+// d<lo -> d1, d in [lo,hi] -> map(x-d-dmin), d>hi -> map(x-hi-dmin), empty interval -> d1.
+// k_so_records folds all of that into, per pixel, one word (d1 < tso) and a D-bit string
+// (bit d = d2(d) < tso); the bit string is a window of a per-row bit vector of the right image
+// stored mirrored, so that increasing d walks increasing bit positions.
 #include "adc_common.cuh"
 
 template <int K>
 struct Piece { static constexpr int G = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1); static constexpr int NP = K / G; };
 
 template <int K>
-__device__ __forceinline__ void load_vec(const float* __restrict__ p, int lane, int Dp, float (&v)[K]) {
+__device__ __forceinline__ void ld_vec(const float* p, int lane, int Dp, float (&v)[K]) {   // generic/shared pointer
     constexpr int G = Piece<K>::G, NP = Piece<K>::NP;
 #pragma unroll
     for (int j = 0; j < NP; j++) {
         const int d = lane * K + j * G;
         if (d < Dp) {
-            if (G == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(p + d)); v[j*G] = t.x; v[j*G+1] = t.y; v[j*G+2] = t.z; v[j*G+3] = t.w; }
-            else if (G == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(p + d)); v[j*G] = t.x; v[j*G+1] = t.y; }
-            else v[j] = __ldg(p + d);
+            if (G == 4) { const float4 t = *reinterpret_cast<const float4*>(p + d); v[j*G] = t.x; v[j*G+1] = t.y; v[j*G+2] = t.z; v[j*G+3] = t.w; }
+            else if (G == 2) { const float2 t = *reinterpret_cast<const float2*>(p + d); v[j*G] = t.x; v[j*G+1] = t.y; }
+            else v[j] = p[d];
         } else {
 #pragma unroll
             for (int g = 0; g < G; g++) v[j * G + g] = 0.f;
@@ -39,7 +48,7 @@ __device__ __forceinline__ void load_vec(const float* __restrict__ p, int lane, 
 }
 
 template <int K>
-__device__ __forceinline__ void store_vec(float* __restrict__ p, int lane, int Dp, const float (&v)[K]) {
+__device__ __forceinline__ void st_vec(float* __restrict__ p, int lane, int Dp, const float (&v)[K]) {
     constexpr int G = Piece<K>::G, NP = Piece<K>::NP;
 #pragma unroll
     for (int j = 0; j < NP; j++) {
@@ -52,39 +61,160 @@ __device__ __forceinline__ void store_vec(float* __restrict__ p, int lane, int D
     }
 }
 
-#define SO_WARPS 4
-#define SO_PF 4   // steps of cost loads kept in flight per warp
+// ---------------------------------------------------------------------------------------------
+// Bit rows of the right image: for variant v in {h-fwd, h-bwd, v-fwd, v-bwd}, bit(xr) of row y says
+// whether the colour distance between right(y,xr) and its predecessor along the path is < tso.
+// Stored mirrored: bit j of the row holds xr = W-1-j.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int so_row_words(int W) { return (W + 31) / 32 + 2; }
 
-template <int K>
+__global__ void __launch_bounds__(128)
+k_so_bitrows(AdcDims dm, int tso, const uint8_t* __restrict__ dmap, unsigned* __restrict__ bitrows) {
+    const int pair = blockIdx.y, y = blockIdx.x;
+    const int W = dm.W, rw = so_row_words(W);
+    const uint8_t* mh = dmap + ((size_t)pair * 4 + 2) * dm.N;   // right image, distance to (y, x-1)
+    const uint8_t* mv = dmap + ((size_t)pair * 4 + 3) * dm.N;   // right image, distance to (y-1, x)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;  // warp = variant
+    unsigned* out = bitrows + (((size_t)pair * 4 + wid) * dm.H + y) * rw;
+    for (int w0 = 0; w0 < rw; w0++) {
+        const int j = w0 * 32 + lane;
+        const int xr = W - 1 - j;
+        bool bit = false;
+        if (xr > 0 && xr < W - 1) {   // the only positions the reference ever looks at (scanline_optimizer.cpp:120)
+            int v;
+            if (wid == 0) v = mh[y * W + xr];                 // +x pass: right[xr] vs right[xr-1]
+            else if (wid == 1) v = mh[y * W + xr + 1];        // -x pass: right[xr] vs right[xr+1]
+            else if (wid == 2) v = y > 0 ? mv[y * W + xr] : 255;            // +y pass: row y vs y-1 (never a path head's successor at y=0)
+            else v = y + 1 < dm.H ? mv[(y + 1) * W + xr] : 255;             // -y pass: row y vs y+1
+            bit = v < tso;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) out[w0] = m;
+    }
+}
+
+// per-pixel record for one pass direction: word 0 = (d1 < tso), words 1.. = bit d -> (d2(d) < tso)
+__host__ __device__ inline int so_rec_words(int Dp) { return ((1 + (Dp + 31) / 32 + 1) + 3) / 4 * 4; }
+
+__global__ void __launch_bounds__(256)
+k_so_records(AdcDims dm, int tso, int sx, int sy, const uint8_t* __restrict__ dmap,
+             const unsigned* __restrict__ bitrows, unsigned* __restrict__ rec) {
+    const int pair = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dm.N) return;
+    const int W = dm.W, D = dm.D, dmin = dm.dmin;
+    const int y = i / W, x = i - y * W;
+    const bool fwd = (sx + sy) > 0;
+    const int pstep = sx + sy * W;
+    const int variant = sx ? (fwd ? 0 : 1) : (fwd ? 2 : 3);
+    const int rw = so_row_words(W), nrec = so_rec_words(dm.Dp);
+    unsigned* out = rec + ((size_t)pair * dm.N + i) * nrec;
+    // d1: this pixel vs the one the path came from (undefined for path heads, which never use it)
+    const uint8_t* ml = dmap + ((size_t)pair * 4 + (sx ? 0 : 1)) * dm.N;
+    const int pi_from = i - pstep;
+    int d1 = 0;
+    if (fwd) d1 = ml[i];
+    else if (pi_from >= 0 && pi_from < dm.N) d1 = ml[pi_from];
+    const unsigned a1 = d1 < tso ? 0xffffffffu : 0u;
+    const int lo = max(0, x - dmin - (W - 2));
+    const int hi = min(D - 1, x - dmin - 1);
+    const unsigned* row = bitrows + (((size_t)pair * 4 + variant) * dm.H + y) * rw;
+    const int j0 = W - 1 - x + dmin;           // bit position of d = 0  (xr = x - dmin)
+    auto window = [&](int d0) -> unsigned {     // bits d0..d0+31 of the string, 0 where out of the row
+        const long long j = (long long)j0 + d0;
+        const long long wlo = j >> 5;            // floor division also for negative j
+        const int sh = (int)(j & 31);
+        const unsigned a = (wlo >= 0 && wlo < rw) ? row[wlo] : 0u;
+        const unsigned b = (wlo + 1 >= 0 && wlo + 1 < rw) ? row[wlo + 1] : 0u;
+        return __funnelshift_r(a, b, sh);
+    };
+    unsigned fill_hi = a1;
+    if (lo <= hi) fill_hi = (window(hi) & 1u) ? 0xffffffffu : 0u;
+    out[0] = a1;
+    const int nw = (dm.Dp + 31) / 32 + 1;
+    for (int w0 = 0; w0 < nw; w0++) {
+        unsigned v;
+        if (lo > hi) v = a1;
+        else {
+            const int d0 = w0 * 32;
+            const unsigned raw = window(d0);
+            // masks of the bits with d < lo and d > hi inside this word
+            const unsigned m_lo = lo <= d0 ? 0u : (lo >= d0 + 32 ? 0xffffffffu : ((1u << (lo - d0)) - 1u));
+            const unsigned m_hi = hi >= d0 + 31 ? 0u : (hi < d0 ? 0xffffffffu : ~((2u << (hi - d0)) - 1u));
+            v = (raw & ~m_lo & ~m_hi) | (a1 & m_lo) | (fill_hi & m_hi);
+        }
+        out[1 + w0] = v;
+    }
+    for (int w0 = 1 + nw; w0 < nrec; w0++) out[w0] = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------
+#define SO_WARPS 4
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <int K, int PF>
 __global__ void __launch_bounds__(SO_WARPS * 32)
 k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
-           const uint8_t* __restrict__ dmap, int sx, int sy) {
+           const unsigned* __restrict__ rec, int sx, int sy) {
+    extern __shared__ __align__(16) unsigned char so_smem[];
     const AdcDims& dm = P.dm;
-    const int lane = threadIdx.x & 31;
-    const int line = blockIdx.x * SO_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int line = blockIdx.x * SO_WARPS + wid;
     const int pair = blockIdx.y;
     const int n_lines = sx ? dm.H : dm.W, n_steps = sx ? dm.W : dm.H;
-    if (line >= n_lines) return;
-    const int W = dm.W, D = dm.D, Dp = dm.Dp, dmin = dm.dmin;
-    const bool fwd = (sx + sy) > 0;
+    if (line >= n_lines) return;   // whole warp; no block-level barriers are used below
+    const int W = dm.W, D = dm.D, Dp = dm.Dp;
     const int pstep = sx + sy * W;  // signed pixel stride along the path
-    const uint8_t* ml = dmap + ((size_t)pair * 4 + (sx ? 0 : 1)) * dm.N;
-    const uint8_t* mr = dmap + ((size_t)pair * 4 + (sx ? 2 : 3)) * dm.N;
+    const int nrec = so_rec_words(Dp);
+    const int cost_chunks = Dp >> 2, rec_chunks = nrec >> 2;      // 16-byte chunks per step
+    const int slot_bytes = (Dp + nrec) * 4;
+    unsigned char* ring = so_smem + (size_t)wid * PF * slot_bytes;
     const float* S = src + (size_t)pair * dm.vol_stride;
     float* O = dst + (size_t)pair * dm.vol_stride;
+    const unsigned* R = rec + (size_t)pair * dm.N * nrec;
 
-    int x = sx ? (sx > 0 ? 0 : W - 1) : line;
-    int y = sy ? (sy > 0 ? 0 : dm.H - 1) : line;
-    int pi = y * W + x;
+    const int x0 = sx ? (sx > 0 ? 0 : W - 1) : line;
+    const int y0 = sy ? (sy > 0 ? 0 : dm.H - 1) : line;
+    int pi = y0 * W + x0;
+
+    auto prefetch = [&](int step) {   // issue the copies of `step` into its ring slot (no commit)
+        const long long p = (long long)(y0 * W + x0) + (long long)step * pstep;
+        unsigned char* slot = ring + (size_t)(step % PF) * slot_bytes;
+        const float* cs = S + (size_t)p * Dp;
+        for (int c = lane; c < cost_chunks; c += 32) cp_async16(slot + c * 16, cs + c * 4);
+        const unsigned* rs = R + (size_t)p * nrec;
+        for (int c = lane; c < rec_chunks; c += 32) cp_async16(slot + Dp * 4 + c * 16, rs + c * 4);
+    };
 
     bool valid[K];
 #pragma unroll
     for (int k = 0; k < K; k++) valid[k] = (lane * K + k) < D;
 
-    // path head: L = C  (scanline_optimizer.cpp:99-100)
+    // start the pipeline, then handle the path head: L = C  (scanline_optimizer.cpp:99-100)
+#pragma unroll
+    for (int j = 1; j <= PF; j++) {
+        if (j < n_steps) prefetch(j);
+        cp_async_commit();           // one group per step, empty groups keep the count uniform
+    }
     float L[K];
-    load_vec<K>(S + (size_t)pi * Dp, lane, Dp, L);
-    store_vec<K>(O + (size_t)pi * Dp, lane, Dp, L);
+    {
+        const float* head = S + (size_t)pi * Dp;
+        constexpr int G = Piece<K>::G, NP = Piece<K>::NP;
+#pragma unroll
+        for (int j = 0; j < NP; j++) {
+            const int d = lane * K + j * G;
+#pragma unroll
+            for (int g = 0; g < G; g++) L[j * G + g] = (d + g < Dp) ? __ldg(head + d + g) : 0.f;
+        }
+    }
+    st_vec<K>(O + (size_t)pi * Dp, lane, Dp, L);
     unsigned key = adc_f2key(ADC_LARGE_F);
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -93,77 +223,93 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
     }
     float minL = adc_key2f(__reduce_min_sync(0xffffffffu, key));
 
-    // software pipeline of the cost loads
-    float buf[SO_PF][K];
-#pragma unroll
-    for (int j = 0; j < SO_PF; j++)
-        if (1 + j < n_steps) load_vec<K>(S + (size_t)(pi + (long long)(1 + j) * pstep) * Dp, lane, Dp, buf[j]);
+    const int bit0 = lane * K;   // first disparity of this lane inside the record's bit string
+    for (int step = 1; step < n_steps; step++) {
+        cp_async_wait<PF - 1>();     // the group of `step` has landed (for this lane's copies)
+        __syncwarp();                // ... and for every other lane's
+        const unsigned char* slot = ring + (size_t)(step % PF) * slot_bytes;
+        float C[K];
+        ld_vec<K>(reinterpret_cast<const float*>(slot), lane, Dp, C);
+        const unsigned* rw = reinterpret_cast<const unsigned*>(slot + Dp * 4);
+        const bool a1 = rw[0] != 0u;
+        const unsigned bits = __funnelshift_r(rw[1 + (bit0 >> 5)], rw[2 + (bit0 >> 5)], bit0 & 31);
+        __syncwarp();                // everyone has read the slot before it is refilled
+        if (step + PF < n_steps) prefetch(step + PF);
+        cp_async_commit();
+        pi += pstep;
 
-    for (int base = 1; base < n_steps; base += SO_PF) {
-#pragma unroll
-        for (int j = 0; j < SO_PF; j++) {
-            const int step = base + j;
-            if (step >= n_steps) break;
-            float C[K];
-#pragma unroll
-            for (int k = 0; k < K; k++) C[k] = buf[j][k];
-            if (step + SO_PF < n_steps)
-                load_vec<K>(S + (size_t)(pi + (long long)(SO_PF + 1) * pstep) * Dp, lane, Dp, buf[j]);
+        const float up = __shfl_up_sync(0xffffffffu, L[K - 1], 1);
+        const float down = __shfl_down_sync(0xffffffffu, L[0], 1);
+        const float left_in = lane == 0 ? ADC_LARGE_F : up;
+        const float right_in = lane == 31 ? ADC_LARGE_F : down;
 
-            const int pi_prev = pi;
-            x += sx; y += sy; pi += pstep;
-            const int d1 = __ldg(ml + (fwd ? pi : pi_prev));
-            const int lo = max(0, x - dmin - (W - 2));
-            const int hi = min(D - 1, x - dmin - 1);
-            const bool a1 = d1 < P.tso;
-
-            const float up = __shfl_up_sync(0xffffffffu, L[K - 1], 1);
-            const float down = __shfl_down_sync(0xffffffffu, L[0], 1);
-            const float left_in = lane == 0 ? ADC_LARGE_F : up;
-            const float right_in = lane == 31 ? ADC_LARGE_F : down;
-
-            float Ln[K];
-            unsigned kmin = adc_f2key(ADC_LARGE_F);
+        float Ln[K];
+        unsigned kmin = adc_f2key(ADC_LARGE_F);
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                const int d = lane * K + k;
-                int d2 = d1;
-                if (lo <= hi && d >= lo) {
-                    const int xr = x - min(d, hi) - dmin;
-                    const int ri = y * W + xr;
-                    d2 = __ldg(mr + (fwd ? ri : ri - pstep));
-                }
-                const bool a2 = d2 < P.tso;
-                const float P1 = (a1 && a2) ? P.p1 : ((a1 || a2) ? P.p1_4 : P.p1_10);
-                const float P2 = (a1 && a2) ? P.p2 : ((a1 || a2) ? P.p2_4 : P.p2_10);
-                const float l1 = L[k];
-                const float l2 = __fadd_rn(k > 0 ? L[k - 1] : left_in, P1);
-                const float l3 = __fadd_rn(k < K - 1 ? L[k + 1] : right_in, P1);
-                const float l4 = __fadd_rn(minL, P2);
-                float v = __fadd_rn(C[k], fminf(fminf(l1, l2), fminf(l3, l4)));
-                v = __fmul_rn(v, 0.5f);
-                Ln[k] = v;
-                if (valid[k]) kmin = min(kmin, adc_f2key(v));
-            }
-            store_vec<K>(O + (size_t)pi * Dp, lane, Dp, Ln);
-#pragma unroll
-            for (int k = 0; k < K; k++) L[k] = valid[k] ? Ln[k] : ADC_LARGE_F;
-            minL = adc_key2f(__reduce_min_sync(0xffffffffu, kmin));
+        for (int k = 0; k < K; k++) {
+            const bool a2 = (bits >> k) & 1u;
+            const float P1 = (a1 && a2) ? P.p1 : ((a1 || a2) ? P.p1_4 : P.p1_10);   // :129-141
+            const float P2 = (a1 && a2) ? P.p2 : ((a1 || a2) ? P.p2_4 : P.p2_10);
+            const float l1 = L[k];
+            const float l2 = __fadd_rn(k > 0 ? L[k - 1] : left_in, P1);
+            const float l3 = __fadd_rn(k < K - 1 ? L[k + 1] : right_in, P1);
+            const float l4 = __fadd_rn(minL, P2);
+            float v = __fadd_rn(C[k], fminf(fminf(l1, l2), fminf(l3, l4)));
+            v = __fmul_rn(v, 0.5f);
+            Ln[k] = v;
+            if (valid[k]) kmin = min(kmin, adc_f2key(v));
         }
+        st_vec<K>(O + (size_t)pi * Dp, lane, Dp, Ln);
+#pragma unroll
+        for (int k = 0; k < K; k++) L[k] = valid[k] ? Ln[k] : ADC_LARGE_F;
+        minL = adc_key2f(__reduce_min_sync(0xffffffffu, kmin));
     }
+    cp_async_wait<0>();
+}
+
+template <int K>
+static int launch_scanline_k(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
+                             cudaStream_t st) {
+    constexpr int PF = 8;
+    const int n_lines = sx ? P.dm.H : P.dm.W;
+    const int slot_bytes = (P.dm.Dp + so_rec_words(P.dm.Dp)) * 4;
+    const size_t smem = (size_t)SO_WARPS * PF * slot_bytes;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_scanline<K, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr_done = true;
+    }
+    dim3 grid((n_lines + SO_WARPS - 1) / SO_WARPS, w.S);
+    k_scanline<K, PF><<<grid, SO_WARPS * 32, smem, st>>>(P, src, dst, w.so_rec, sx, sy);
+    return 0;
+}
+
+void adc_launch_so_bitrows(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
+    dim3 grid(P.dm.H, w.S);
+    k_so_bitrows<<<grid, 128, 0, st>>>(P.dm, P.tso, w.dmap, w.so_bitrows);
+    ++*launches;
 }
 
 int adc_launch_scanline(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
                         cudaStream_t st, unsigned long long* launches) {
-    const int n_lines = sx ? P.dm.H : P.dm.W;
-    dim3 grid((n_lines + SO_WARPS - 1) / SO_WARPS, w.S);
+    dim3 grid((P.dm.N + 255) / 256, w.S);
+    k_so_records<<<grid, 256, 0, st>>>(P.dm, P.tso, sx, sy, w.dmap, w.so_bitrows, w.so_rec);
     const int K = (P.dm.Dp + 31) / 32;
+    int rc = 1;
     switch (K) {
-#define SO_CASE(KK) case KK: k_scanline<KK><<<grid, SO_WARPS * 32, 0, st>>>(P, src, dst, w.dmap, sx, sy); break;
-        SO_CASE(1) SO_CASE(2) SO_CASE(3) SO_CASE(4) SO_CASE(5) SO_CASE(6) SO_CASE(7) SO_CASE(8)
-#undef SO_CASE
+        case 1: rc = launch_scanline_k<1>(P, w, src, dst, sx, sy, st); break;
+        case 2: rc = launch_scanline_k<2>(P, w, src, dst, sx, sy, st); break;
+        case 3: rc = launch_scanline_k<3>(P, w, src, dst, sx, sy, st); break;
+        case 4: rc = launch_scanline_k<4>(P, w, src, dst, sx, sy, st); break;
+        case 5: rc = launch_scanline_k<5>(P, w, src, dst, sx, sy, st); break;
+        case 6: rc = launch_scanline_k<6>(P, w, src, dst, sx, sy, st); break;
+        case 7: rc = launch_scanline_k<7>(P, w, src, dst, sx, sy, st); break;
+        case 8: rc = launch_scanline_k<8>(P, w, src, dst, sx, sy, st); break;
         default: return 1;  // D > 256 not supported by the warp-per-line kernel
     }
-    ++*launches;
-    return 0;
+    *launches += 2;
+    return rc;
 }
+
+size_t adc_so_rec_bytes(const AdcDims& dm) { return (size_t)dm.N * so_rec_words(dm.Dp) * 4; }
+size_t adc_so_bitrow_bytes(const AdcDims& dm) { return (size_t)4 * dm.H * so_row_words(dm.W) * 4; }

@@ -11,7 +11,7 @@ import adc_testlib as T
 left, right = T.load_cone()
 h, w, _ = left.shape
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-for S, lanes in ((8, 3), (4, 3), (16, 2), (2, 4)):
+for S, lanes in ((16, 3), (8, 3), (16, 2), (32, 2)):
     eng = A.Engine(w, h, A.ADCensusOption(), wave_pairs=S, lanes=lanes)
     dl = torch.from_numpy(np.repeat(left[None], n, 0)).cuda()
     dr = torch.from_numpy(np.repeat(right[None], n, 0)).cuda()
@@ -34,4 +34,5 @@ for S, lanes in ((8, 3), (4, 3), (16, 2), (2, 4)):
 eng = A.Engine(w, h, A.ADCensusOption())
 for _ in range(3):
     d = eng.match(left, right)
+print("voting counters [mism, occl, rounds, evals]:", eng.counters()[:4])
 print("single-pair stage ms (cost, aggr, so, wta, refine, out):", [round(x, 3) for x in eng.last_stage_ms()])
