@@ -17,6 +17,7 @@
 
 #define ADC_INVALID_F (__int_as_float(0x7f800000))  // +inf  (adcensus_types.h:33)
 #define ADC_LARGE_F 99999.0f                         // adcensus_types.h:35
+#define ADC_CNT 16                                   // ints of per-pair counters
 
 struct AdcDims {
     int W, H, D, Dp;        // Dp: padded disparity stride (multiple of 4)
@@ -68,12 +69,13 @@ struct AdcWave {            // device pointers of one wave (S pairs)
     float* disp_l; float* disp_r; float* disp_t;
     uint8_t* label; uint8_t* flag;
     int* pend;              // [S][2][N] mismatch / occlusion pixel lists (raster order)
-    int* counters;          // [S][8]: 0,1 list sizes; 2 voting rounds; 3 voting evaluations
+    int* counters;          // [S][ADC_CNT]: 0,1 list sizes; 2 voting rounds; 3 voting evaluations; 4.. flags/queues
     int* rowcnt;            // [S][2][H] per-row list counts / offsets
     unsigned* so_bitrows;   // [S][4][H][row words] mirrored per-row bit vectors of the right image (scanline optimiser)
     unsigned* so_rec;       // [S][N][rec words] per-pixel penalty records of the pass being run
     int* tile_stamp;        // [S][tiles] region voting: epoch of the last change near a 16x16 tile
-    int* last_eval;         // [S][N]     region voting: epoch of a pixel's last evaluation
+    int* last_eval;         // [S][N]     region voting: epoch of a pixel's (or tile's) last evaluation
+    uint8_t* vote_dq;       // [S][2][N]  region voting: rounded disparity index per pixel, NEW and OLD state
     const float* lut_ad;    // [766]  (1 - exp(-(s/3)/lambda_ad)) + 1, host libm expf
     const float* lut_cen;   // [64]   exp(-h/lambda_census)
     const double* ray_sin; const double* ray_cos; // [16] host libm sin/cos of the accumulated angles
@@ -100,4 +102,6 @@ void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, un
 // k = 0: mismatch list, k = 1: occlusion list; reads disp_l, writes disp_t
 void adc_launch_interp_list(const AdcParams& P, const AdcWave& w, int k, cudaStream_t st, unsigned long long* launches);
 void adc_launch_discontinuity(const AdcParams& P, const AdcWave& w, const float* vol, cudaStream_t st, unsigned long long* launches);
-void adc_launch_median(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
+// in-place-equivalent 3x3 median: reads `in`, writes `out` (different buffers); non-zero if H is too large
+int adc_launch_median(const AdcParams& P, const AdcWave& w, const float* in, float* out, cudaStream_t st,
+                      unsigned long long* launches);

@@ -122,7 +122,8 @@ size_t carve_lane(void* base, const AdcDims& dm, int S, AdcWave* w) {
     t.label = c.take<uint8_t>((size_t)S * N);
     t.flag = c.take<uint8_t>((size_t)S * N);
     t.pend = c.take<int>((size_t)S * 2 * N);
-    t.counters = c.take<int>((size_t)S * 8);
+    t.counters = c.take<int>((size_t)S * ADC_CNT);
+    t.vote_dq = c.take<uint8_t>((size_t)S * 2 * N);
     t.rowcnt = c.take<int>((size_t)S * 2 * dm.H);
     t.so_bitrows = c.take<unsigned>((size_t)S * adc_so_bitrow_bytes(dm) / 4);
     t.so_rec = c.take<unsigned>((size_t)S * adc_so_rec_bytes(dm) / 4);
@@ -254,7 +255,7 @@ int enqueue_pipeline(adc_engine* e, Lane& ln, int nS, int last_stage, cudaEvent_
     }
     if (stop(ADC_STAGE_OUTLIER)) return ADC_OK;
     if (e->opt.do_filling) {  // gates voting AND interpolation (ADCensusStereo.cpp:183)
-        CK(cudaMemsetAsync(w.counters, 0, (size_t)nS * 8 * sizeof(int), st));
+        CK(cudaMemsetAsync(w.counters, 0, (size_t)nS * ADC_CNT * sizeof(int), st));
         adc_launch_build_lists(P, w, st, L);
         adc_launch_voting(P, w, st, L);
         if (stop(ADC_STAGE_VOTE)) return ADC_OK;
@@ -269,7 +270,10 @@ int enqueue_pipeline(adc_engine* e, Lane& ln, int nS, int last_stage, cudaEvent_
     }
     if (e->opt.do_discontinuity_adjustment) adc_launch_discontinuity(P, w, A, st, L);
     if (stop(ADC_STAGE_DISC)) return ADC_OK;
-    adc_launch_median(P, w, st, L);
+    // median: disp_l -> disp_t, then back so that disp_l always holds the current map
+    if (adc_launch_median(P, w, w.disp_l, w.disp_t, st, L))
+        return fail(ADC_ERR_UNSUPPORTED, "image height %d exceeds the median kernel's limit of 2048 rows", P.dm.H);
+    CK(cudaMemcpyAsync(w.disp_l, w.disp_t, mapN * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (ev) CK(cudaEventRecord(ev[5], st));
     e->dbg_stage = ADC_STAGE_MEDIAN;
     CK(cudaGetLastError());

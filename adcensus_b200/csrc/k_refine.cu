@@ -133,7 +133,7 @@ k_list_row_scan(AdcDims dm, int* __restrict__ rowcnt, int* __restrict__ counters
         if (y < dm.H) rc[y] = base + inc - v;
         base += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) counters[pair * 8 + k] = base;
+    if (lane == 0) counters[pair * ADC_CNT + k] = base;
 }
 
 __global__ void __launch_bounds__(128)
@@ -212,8 +212,8 @@ __device__ __forceinline__ void rv_stamp_tiles(int* tiles, int tw, int th, int x
 #define RV_CLUSTER 8
 
 __global__ void __cluster_dims__(RV_CLUSTER, 1, 1) __launch_bounds__(RV_THREADS)
-k_region_voting(AdcParams P, const uchar4* __restrict__ arms, float* disp_old, float* disp_new,
-                uint8_t* label, int* pend, int* counters, int* tile_stamp, int* last_eval) {
+k_region_voting_global(AdcParams P, const uchar4* __restrict__ arms, float* disp_old, float* disp_new,
+                       uint8_t* label, int* pend, int* counters, int* tile_stamp, int* last_eval) {
     __shared__ int s_hist[RV_WARPS][RV_MAXD];
     __shared__ int s_tot[RV_WARPS];
     const AdcDims& dm = P.dm;
@@ -231,7 +231,7 @@ k_region_voting(AdcParams P, const uchar4* __restrict__ arms, float* disp_old, f
     uint8_t* lab = label + (size_t)pair * dm.N;
     int* tiles = tile_stamp + (size_t)pair * tw * th;
     int* evalep = last_eval + (size_t)pair * dm.N;
-    int* cnt = counters + pair * 8;   // 0,1: list sizes   2: rounds   3: evaluations   4..6: change flags (mod 3)
+    int* cnt = counters + pair * ADC_CNT;   // 0,1: list sizes   2: rounds   3: evaluations   4..6: change flags (mod 3)
     int n_list[2] = {__ldcg(cnt + 0), __ldcg(cnt + 1)};
     int rounds_total = 0, evals = 0;
     int* hist = s_hist[wid];
@@ -334,11 +334,251 @@ k_region_voting(AdcParams P, const uchar4* __restrict__ arms, float* disp_old, f
     if (gtid == 0) __stcg(cnt + 2, rounds_total);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Shared-memory tile version of the same fixed point (the fast path).  Only the rounded
+// disparity index matters for a vote, so the state is kept as one byte per pixel (0..253 = index,
+// 254 = valid but outside [0,D), 255 = invalid) in two global byte maps (OLD/NEW).  The image is
+// cut into 64x64 tiles; in every round the CTAs of the cluster pull *active* tiles (stamped since
+// their last evaluation) from a queue, stage the tile plus a halo of `reach` pixels -- state bytes
+// and horizontal arms -- into shared memory with coalesced loads, and iterate the tile's pending
+// pixels to a local fixed point entirely out of shared memory (~30-cycle accesses instead of
+// dependent L2 round trips).  Changes are written through to the global NEW map and stamp the
+// neighbouring tiles; the rounds end when a whole round changes nothing, exactly as above.
+// ---------------------------------------------------------------------------------------------
+#define RV_T 64
+#define RV_MAXREACH 34
+#define RV_INNER 4
+
+__global__ void k_vote_encode(AdcDims dm, const float* __restrict__ disp, uint8_t* __restrict__ dq) {
+    const int pair = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dm.N) return;
+    const float d = disp[(size_t)pair * dm.N + i];
+    uint8_t v = 255;
+    if (d != ADC_INVALID_F) {
+        const int di = (int)roundf(d) - dm.dmin;
+        v = (di >= 0 && di < dm.D && di < 254) ? (uint8_t)di : (uint8_t)254;
+    }
+    dq[((size_t)pair * 2 + 0) * dm.N + i] = v;
+    dq[((size_t)pair * 2 + 1) * dm.N + i] = v;
+}
+
+__global__ void __cluster_dims__(RV_CLUSTER, 1, 1) __launch_bounds__(RV_THREADS)
+k_region_voting_tiles(AdcParams P, const uchar4* __restrict__ arms, float* disp_old, float* disp_new,
+                      uint8_t* dq, uint8_t* label, int* pend, int* counters, int* tile_stamp, int* tile_eval) {
+    extern __shared__ __align__(16) unsigned char rv_smem[];
+    const AdcDims& dm = P.dm;
+    const int reach = max(P.L1, 0);
+    const int E = RV_T + 2 * reach, ES = E + 1;         // staged edge and padded row stride (words)
+    uchar4* tile = reinterpret_cast<uchar4*>(rv_smem);                                   // [E][ES] {new, old, left, right}
+    int* s_hist_base = reinterpret_cast<int*>(rv_smem + (size_t)E * ES * 4);             // [RV_WARPS][RV_MAXD]
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_hist_base + RV_WARPS * RV_MAXD);  // [RV_T*RV_T]
+    __shared__ int s_tot[RV_WARPS];
+    __shared__ int s_tile, s_count, s_local_changed;
+
+    const int pair = blockIdx.x / RV_CLUSTER;
+    const int crank = blockIdx.x % RV_CLUSTER;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int gwarp = crank * RV_WARPS + wid, n_gwarps = RV_CLUSTER * RV_WARPS;
+    const int gtid = crank * RV_THREADS + tid, n_gthreads = RV_CLUSTER * RV_THREADS;
+    const int W = dm.W, H = dm.H, D = dm.D;
+    const int ntx = (W + RV_T - 1) / RV_T, nty = (H + RV_T - 1) / RV_T, n_tiles = ntx * nty;
+    const uchar4* A = arms + (size_t)pair * dm.N;
+    float* d_old = disp_old + (size_t)pair * dm.N;
+    float* d_new = disp_new + (size_t)pair * dm.N;
+    uint8_t* q_new = dq + ((size_t)pair * 2 + 0) * dm.N;
+    uint8_t* q_old = dq + ((size_t)pair * 2 + 1) * dm.N;
+    uint8_t* lab = label + (size_t)pair * dm.N;
+    int* stamps = tile_stamp + (size_t)pair * n_tiles;
+    int* evals_ep = tile_eval + (size_t)pair * 2 * n_tiles;
+    int* cnt = counters + pair * ADC_CNT;  // 0,1 list sizes; 2 rounds; 3 evaluations; 4..6 change flags; 7..9 tile queues
+    int n_list[2] = {__ldcg(cnt + 0), __ldcg(cnt + 1)};
+    int rounds_total = 0, evals = 0;
+    int* hist = s_hist_base + wid * RV_MAXD;
+    const int grp = lane >> 3, sub = lane & 7;
+
+    for (int i = gtid; i < n_tiles; i += n_gthreads) { __stcg(stamps + i, 0); __stcg(evals_ep + i, 0); __stcg(evals_ep + n_tiles + i, 0); }
+    if (gtid < 6) __stcg(cnt + 4 + gtid, 0);
+    int epoch = 1, rnd = 0;
+    cluster_sync_all();
+
+    auto stamp_around = [&](int x, int y, int self_tile) {   // all lanes of the warp call this
+        const int tx0 = max(0, (x - reach) / RV_T), tx1 = min(ntx - 1, (x + reach) / RV_T);
+        const int ty0 = max(0, (y - reach) / RV_T), ty1 = min(nty - 1, (y + reach) / RV_T);
+        const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
+        for (int i = lane; i < nt; i += 32) {
+            const int t = (ty0 + i / nx) * ntx + tx0 + i % nx;
+            if (t != self_tile) __stcg(stamps + t, epoch);
+        }
+    };
+
+    for (int it = 0; it < 5; it++) {
+        for (int k = 0; k < 2; k++) {
+            int* list = pend + ((size_t)pair * 2 + k) * dm.N;
+            const int n = n_list[k];
+            if (n == 0) continue;  // uniform across the cluster
+            bool any_fill = false;
+            while (true) {
+                if (gtid == 0) { __stcg(cnt + 4 + (rnd + 1) % 3, 0); __stcg(cnt + 7 + (rnd + 1) % 3, 0); }
+                bool cta_changed = false;
+                while (true) {
+                    // ---- next tile from the round's queue
+                    __syncthreads();
+                    if (tid == 0) s_tile = atomicAdd(cnt + 7 + rnd % 3, 1);
+                    __syncthreads();
+                    const int t = s_tile;
+                    if (t >= n_tiles) break;
+                    if (__ldcg(stamps + t) < __ldcg(evals_ep + k * n_tiles + t)) continue;   // nothing changed near it since
+                    const int ty0 = (t / ntx) * RV_T, tx0 = (t % ntx) * RV_T;
+                    // ---- pending pixels of class k inside the tile, raster order
+                    int base = 0;
+                    for (int c0 = 0; c0 < RV_T * RV_T; c0 += RV_THREADS) {
+                        const int li = c0 + tid, ly = li / RV_T, lx = li % RV_T;
+                        const int gy = ty0 + ly, gx = tx0 + lx;
+                        const bool f = gy < H && gx < W && __ldcg(lab + gy * W + gx) == k + 1;   // L2: other CTAs clear labels at commit
+                        const unsigned bm = __ballot_sync(0xffffffffu, f);
+                        if (lane == 0) s_tot[wid] = __popc(bm);
+                        __syncthreads();
+                        int off = base, tot = 0;
+                        for (int w2 = 0; w2 < RV_WARPS; w2++) { const int c = s_tot[w2]; if (w2 < wid) off += c; tot += c; }
+                        if (f) s_list[off + __popc(bm & ((1u << lane) - 1u))] = (unsigned short)li;
+                        base += tot;
+                        __syncthreads();
+                    }
+                    const int count = base;
+                    if (count == 0) { if (tid == 0) __stcg(evals_ep + k * n_tiles + t, epoch); continue; }
+                    // ---- stage state bytes and horizontal arms of the tile + halo
+                    for (int i = tid; i < E * E; i += RV_THREADS) {
+                        const int ry = i / E, rx = i - ry * E;
+                        const int gy = ty0 - reach + ry, gx = tx0 - reach + rx;
+                        uchar4 v = make_uchar4(255, 255, 0, 0);
+                        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                            const int g = gy * W + gx;
+                            const uchar4 a = __ldg(A + g);
+                            v = make_uchar4(__ldcg(q_new + g), __ldcg(q_old + g), a.x, a.y);
+                        }
+                        tile[ry * ES + rx] = v;
+                    }
+                    __syncthreads();
+                    // ---- local fixed point
+                    bool capped = false;
+                    for (int inner = 0; inner < RV_INNER; inner++) {
+                        if (tid == 0) s_local_changed = 0;
+                        __syncthreads();
+                        for (int idx = wid; idx < count; idx += RV_WARPS) {
+                            const int li = s_list[idx], ly = li / RV_T, lx = li % RV_T;
+                            const int gy = ty0 + ly, gx = tx0 + lx, p = gy * W + gx;
+                            evals++;
+                            for (int b = lane; b < D; b += 32) hist[b] = 0;
+                            __syncwarp();
+                            const uchar4 a = __ldg(A + p);
+                            const int cy = ly + reach, cx = lx + reach;
+                            for (int tt = -(int)a.z + grp; tt <= (int)a.w; tt += 4) {
+                                const uchar4* rowp = tile + (cy + tt) * ES + cx;
+                                const uchar4 c0 = rowp[0];
+                                for (int ss = -(int)c0.z + sub; ss <= (int)c0.w; ss += 8) {
+                                    const uchar4 c = rowp[ss];
+                                    const bool before = (tt < 0) || (tt == 0 && ss < 0);
+                                    const int dv = before ? c.x : c.y;
+                                    if (dv < 254) atomicAdd(&hist[dv], 1);
+                                }
+                            }
+                            __syncwarp();
+                            int peak = 0, best = 0x7fffffff, total = 0;
+                            for (int b = lane; b < D; b += 32) {
+                                const int h = hist[b];
+                                if (peak < h) { peak = h; best = b; }
+                                total += h;
+                            }
+                            const int gpeak = __reduce_max_sync(0xffffffffu, peak);
+                            const int gbest = __reduce_min_sync(0xffffffffu, peak == gpeak ? best : 0x7fffffff);
+                            total = __reduce_add_sync(0xffffffffu, total);
+                            int r = 255;
+                            if (gpeak > 0 && total > P.irv_ts &&
+                                __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th)
+                                r = gbest;
+                            uchar4* self = tile + cy * ES + cx;
+                            const bool changed = r != (int)self->x;
+                            __syncwarp();
+                            if (changed) {
+                                if (lane == 0) { self->x = (unsigned char)r; __stcg(q_new + p, (uint8_t)r); s_local_changed = 1; }
+                                stamp_around(gx, gy, t);
+                                cta_changed = true;
+                            }
+                        }
+                        __syncthreads();
+                        const int lc = s_local_changed;
+                        __syncthreads();
+                        if (!lc) break;
+                        if (inner == RV_INNER - 1) capped = true;
+                    }
+                    if (tid == 0) {
+                        __stcg(evals_ep + k * n_tiles + t, epoch);
+                        if (capped) __stcg(stamps + t, epoch);   // not yet locally consistent: look again next round
+                    }
+                }
+                if (cta_changed && tid == 0) __stcg(cnt + 4 + rnd % 3, 1);
+                cluster_sync_all();
+                const int ch = __ldcg(cnt + 4 + rnd % 3);
+                rounds_total++;
+                epoch++;
+                rnd++;
+                if (!ch) break;
+                any_fill = true;
+            }
+            if (!any_fill) continue;
+            // ---- commit: OLD <- NEW for filled pixels (float maps too), stamp, erase from the list
+            for (int idx = gwarp; idx < n; idx += n_gwarps) {
+                const int p = __ldcg(list + idx);
+                const int v = __ldcg(q_new + p);
+                if (v != 255) {
+                    if (lane == 0) {
+                        const float f = (float)(v + dm.dmin);
+                        __stcg(q_old + p, (uint8_t)v);
+                        __stcg(d_old + p, f);
+                        __stcg(d_new + p, f);
+                        __stcg(lab + p, (uint8_t)0);
+                    }
+                    const int y = p / W;
+                    stamp_around(p - y * W, y, -1);
+                }
+            }
+            epoch++;
+            cluster_sync_all();
+            if (crank == 0) {
+                const int kept = rv_compact_invalid(n, list, d_old, s_tot);
+                if (tid == 0) __stcg(cnt + k, kept);
+            }
+            cluster_sync_all();
+            n_list[k] = __ldcg(cnt + k);
+        }
+    }
+    evals = __reduce_add_sync(0xffffffffu, lane == 0 ? evals : 0);
+    if (lane == 0) atomicAdd(cnt + 3, evals);
+    if (gtid == 0) __stcg(cnt + 2, rounds_total);
+}
+
 void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
     // disp_l = committed state (OLD), disp_t = working copy (NEW); both hold the post-outlier map here
-    k_region_voting<<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.disp_l, w.disp_t, w.label, w.pend, w.counters,
-                                                             w.tile_stamp, w.last_eval);
-    ++*launches;
+    const int reach = P.L1 > 0 ? P.L1 : 0;
+    if (P.dm.D <= 254 && reach <= RV_MAXREACH) {
+        const int E = RV_T + 2 * reach;
+        const size_t smem = (size_t)E * (E + 1) * 4 + (size_t)RV_WARPS * RV_MAXD * 4 + (size_t)RV_T * RV_T * 2;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(k_region_voting_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            attr_done = true;
+        }
+        dim3 grid((P.dm.N + 255) / 256, w.S);
+        k_vote_encode<<<grid, 256, 0, st>>>(P.dm, w.disp_l, w.vote_dq);
+        k_region_voting_tiles<<<w.S * RV_CLUSTER, RV_THREADS, smem, st>>>(P, w.arms, w.disp_l, w.disp_t, w.vote_dq, w.label,
+                                                                         w.pend, w.counters, w.tile_stamp, w.last_eval);
+        *launches += 2;
+    } else {
+        k_region_voting_global<<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.disp_l, w.disp_t, w.label, w.pend,
+                                                                        w.counters, w.tile_stamp, w.last_eval);
+        ++*launches;
+    }
 }
 
 // =============================================================================================
@@ -358,7 +598,7 @@ k_interpolate(AdcParams P, int k, const uint8_t* __restrict__ bgr, const float* 
               const double* __restrict__ ray_sin, const double* __restrict__ ray_cos) {
     const AdcDims& dm = P.dm;
     const int pair = blockIdx.y;
-    const int n = counters[pair * 8 + k];
+    const int n = counters[pair * ADC_CNT + k];
     const int* list = pend + ((size_t)pair * 2 + k) * dm.N;
     const uint8_t* left = bgr + (size_t)pair * 2 * dm.N * 3;
     const float* d_old = disp_old + (size_t)pair * dm.N;
@@ -491,8 +731,13 @@ void adc_launch_discontinuity(const AdcParams& P, const AdcWave& w, const float*
 //    per step reproduces the sequential scan exactly (every window element of step t was produced
 //    at a step != t).  Window = in-image neighbours, sorted, element n/2 (9->[4], 6->[3], 4->[2]);
 //    realised as the median of 9 after padding with -inf/+inf so that the rank is preserved.
+//    Data movement: one thread per row.  "Original" values come from the untouched input map
+//    (read-only, so they cache in L1), "filtered" values of the row above come from a 4-deep
+//    per-row ring in shared memory written by the neighbouring thread, the filtered left
+//    neighbour is the thread's own previous result; the output goes to a second map.
 // =============================================================================================
 #define MED_THREADS 1024
+#define MED_ROWS 2   // rows per thread -> images up to 2048 rows
 
 __device__ __forceinline__ void cswap(float& a, float& b) { const float lo = fminf(a, b), hi = fmaxf(a, b); a = lo; b = hi; }
 
@@ -509,45 +754,70 @@ __device__ __forceinline__ float median9(float v[9]) {
 }
 
 __global__ void __launch_bounds__(MED_THREADS)
-k_median_wavefront(AdcDims dm, float* disp) {
+k_median_wavefront(AdcDims dm, const float* __restrict__ in, float* __restrict__ out) {
+    extern __shared__ float med_ring[];   // [H][4] filtered values of each row, indexed by column & 3
     const int pair = blockIdx.x;
-    float* img = disp + (size_t)pair * dm.N;
+    const float* src = in + (size_t)pair * dm.N;
+    float* dst = out + (size_t)pair * dm.N;
     const int W = dm.W, H = dm.H;
     const float NINF = __int_as_float(0xff800000), PINF = ADC_INVALID_F;
     const int n_steps = W + 2 * H - 2;
+    float left_new[MED_ROWS];
+#pragma unroll
+    for (int r = 0; r < MED_ROWS; r++) left_new[r] = 0.f;
     for (int t = 0; t < n_steps; t++) {
-        for (int y = threadIdx.x; y < H; y += MED_THREADS) {
+        float res[MED_ROWS];
+        bool act[MED_ROWS];
+#pragma unroll
+        for (int r = 0; r < MED_ROWS; r++) {
+            const int y = threadIdx.x + r * MED_THREADS;
             const int x = t - 2 * y;
-            if (x < 0 || x >= W) continue;
+            act[r] = y < H && x >= 0 && x < W;
+            res[r] = 0.f;
+            if (!act[r]) continue;
+            const bool up = y > 0, dn = y + 1 < H, lf = x > 0, rt = x + 1 < W;
             float v[9];
-            int n = 0;
-#pragma unroll
-            for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-                for (int dx = -1; dx <= 1; dx++) {
-                    const int yy = y + dy, xx = x + dx;
-                    const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
-                    v[(dy + 1) * 3 + dx + 1] = in ? img[yy * W + xx] : PINF;
-                    n += in;
-                }
-            // n in {9,6,4}: wanted rank n/2 of the n real values == rank 4 of 9 after adding
-            // (4 - n/2) values of -inf and the rest +inf.  Out-of-image slots were filled with +inf;
-            // turn (4 - n/2) of them into -inf.
+            const float* ring_up = med_ring + (size_t)(y - 1) * 4;
+            v[0] = (up && lf) ? ring_up[(x - 1) & 3] : PINF;
+            v[1] = up ? ring_up[x & 3] : PINF;
+            v[2] = (up && rt) ? ring_up[(x + 1) & 3] : PINF;
+            v[3] = lf ? left_new[r] : PINF;
+            v[4] = __ldg(src + y * W + x);
+            v[5] = rt ? __ldg(src + y * W + x + 1) : PINF;
+            v[6] = (dn && lf) ? __ldg(src + (y + 1) * W + x - 1) : PINF;
+            v[7] = dn ? __ldg(src + (y + 1) * W + x) : PINF;
+            v[8] = (dn && rt) ? __ldg(src + (y + 1) * W + x + 1) : PINF;
+            const int n = (1 + (int)up + (int)dn) * (1 + (int)lf + (int)rt);
+            // wanted rank n/2 of the n real values == rank 4 of 9 once (4 - n/2) of the absent slots
+            // hold -inf and the others +inf
             int need = 4 - n / 2;
+            const bool present[9] = {up && lf, up, up && rt, lf, true, rt, dn && lf, dn, dn && rt};
 #pragma unroll
-            for (int j = 0; j < 9; j++) {
-                const int dy = j / 3 - 1, dx = j % 3 - 1;
-                const int yy = y + dy, xx = x + dx;
-                const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
-                if (!in && need > 0) { v[j] = NINF; need--; }
-            }
-            img[y * W + x] = median9(v);
+            for (int j = 0; j < 9; j++)
+                if (!present[j] && need > 0) { v[j] = NINF; need--; }
+            res[r] = median9(v);
+        }
+        // the ring slot (x & 3) of row y still holds column x-4, which row y+1 read for the last time
+        // at step t-1 (as its column (x-4)+1+... <= x-3): safe to overwrite after this step's reads
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < MED_ROWS; r++) {
+            if (!act[r]) continue;
+            const int y = threadIdx.x + r * MED_THREADS;
+            const int x = t - 2 * y;
+            med_ring[(size_t)y * 4 + (x & 3)] = res[r];
+            left_new[r] = res[r];
+            dst[y * W + x] = res[r];
         }
         __syncthreads();
     }
 }
 
-void adc_launch_median(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
-    k_median_wavefront<<<w.S, MED_THREADS, 0, st>>>(P.dm, w.disp_l);
+int adc_launch_median(const AdcParams& P, const AdcWave& w, const float* in, float* out, cudaStream_t st,
+                      unsigned long long* launches) {
+    if (P.dm.H > MED_THREADS * MED_ROWS) return 1;
+    const size_t smem = (size_t)P.dm.H * 4 * sizeof(float);
+    k_median_wavefront<<<w.S, MED_THREADS, smem, st>>>(P.dm, in, out);
     ++*launches;
+    return 0;
 }
