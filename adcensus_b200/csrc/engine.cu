@@ -573,6 +573,42 @@ int adc_get_config(const adc_engine* e, adc_config* out) {
     return ADC_OK;
 }
 
+// ---- per-kernel timing for the roofline figures of bench.py ------------------------------------
+// Re-launches ONE kernel of the pipeline `reps` times on lane 0's wave buffers (which hold whatever
+// the last batch left there; every kernel below is data-oblivious in its memory traffic except for
+// the arm lengths, which are real) and reports the mean device time per launch, measured with CUDA
+// events on the lane's own stream, plus the algorithmic bytes one launch moves (SURVEY.md 8d model).
+int adc_profile_kernel(adc_engine* e, int32_t kernel_id, int32_t reps, float* avg_ms, double* algorithmic_bytes) {
+    if (!e || !avg_ms || reps <= 0) return fail(ADC_ERR_ARG, "adc_profile_kernel: bad arguments");
+    CK(cudaSetDevice(e->cfg.device));
+    Lane& ln = e->lanes[0];
+    const AdcParams& P = e->P;
+    const AdcWave w = wave_view(e, ln, e->S);
+    const double V = (double)P.dm.N * P.dm.D * 4.0, N = (double)P.dm.N;
+    double bytes = 0;
+    CK(cudaStreamSynchronize(ln.st));
+    cudaEvent_t e0 = e->ev_stage[0], e1 = e->ev_stage[1];
+    for (int r = -1; r < reps; r++) {   // r = -1: warm-up launch
+        if (r == 0) CK(cudaEventRecord(e0, ln.st));
+        switch (kernel_id) {
+            case 0: adc_launch_cost(P, w, w.volB, ln.st, &e->launches); bytes = V + 6 * N + 16 * N; break;
+            case 1: adc_launch_arm_sum(P, w, w.volA, w.volB, 0, nullptr, ln.st, &e->launches); bytes = 2 * V + 4 * N; break;
+            case 2: adc_launch_arm_sum(P, w, w.volA, w.volB, 1, w.sup_h, ln.st, &e->launches); bytes = 2 * V + 6 * N; break;
+            case 3: if (adc_launch_scanline(P, w, w.volA, w.volB, 1, 0, ln.st, &e->launches)) return fail(ADC_ERR_UNSUPPORTED, "scanline"); bytes = 2 * V + 6 * N; break;
+            case 4: if (adc_launch_scanline(P, w, w.volA, w.volB, 0, 1, ln.st, &e->launches)) return fail(ADC_ERR_UNSUPPORTED, "scanline"); bytes = 2 * V + 6 * N; break;
+            case 5: adc_launch_wta(P, w, w.volA, ln.st, &e->launches); bytes = V + 8 * N; break;
+            default: return fail(ADC_ERR_ARG, "adc_profile_kernel: unknown kernel id %d", kernel_id);
+        }
+    }
+    CK(cudaEventRecord(e1, ln.st));
+    CK(cudaStreamSynchronize(ln.st));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *avg_ms = ms / reps;
+    if (algorithmic_bytes) *algorithmic_bytes = bytes * e->S;
+    return ADC_OK;
+}
+
 // ---- debug taps -----------------------------------------------------------------------------
 int adc_debug_run(adc_engine* e, const uint8_t* img_left, const uint8_t* img_right, int32_t last_stage) {
     if (!e) return fail(ADC_ERR_ARG, "adc_debug_run: engine is NULL");

@@ -666,7 +666,7 @@ void adc_launch_interp_list(const AdcParams& P, const AdcWave& w, int k, cudaStr
 //    disparity map, then per row a strictly sequential left-to-right pass (pixel x may copy from
 //    x-1, which may itself have just been changed) -> one thread per row.  The reference indexes
 //    the cost volume with lround(d) without subtracting dmin (multistep_refiner.cpp:331); indices
-//    outside [0,D) are undefined behaviour there and skipped here (as in oracle/adc_oracle.c).
+//    outside [0,D) are undefined behaviour there and skipped here (the CPU checker does the same).
 // =============================================================================================
 __global__ void k_edge_mask(AdcDims dm, const float* __restrict__ disp, uint8_t* __restrict__ edge) {
     const int pair = blockIdx.y;

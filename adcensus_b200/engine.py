@@ -92,6 +92,7 @@ def load_library() -> ctypes.CDLL:
     L.adc_launch_count.restype = ctypes.c_uint64
     L.adc_last_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 6)]
     L.adc_get_config.argtypes = [vp, ctypes.POINTER(_Config)]
+    L.adc_profile_kernel.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]
     L.adc_last_error.restype = ctypes.c_char_p
     L.adc_version.restype = ctypes.c_char_p
     L.adc_debug_run.argtypes = [vp, u8p, u8p, i32]
@@ -190,6 +191,14 @@ class Engine:
         out = (ctypes.c_float * 6)()
         _check(self._L.adc_last_stage_ms(self._h, ctypes.byref(out)))
         return list(out)
+
+    PROFILE_KERNELS = {"cost_volume": 0, "arm_sum_h": 1, "arm_sum_v_div": 2, "scanline_x": 3, "scanline_y": 4, "wta": 5}
+
+    def profile_kernel(self, name: str, reps: int = 5):
+        """(mean ms per launch over one wave, algorithmic bytes per launch) of one pipeline kernel."""
+        ms, by = ctypes.c_float(), ctypes.c_double()
+        _check(self._L.adc_profile_kernel(self._h, self.PROFILE_KERNELS[name], reps, ctypes.byref(ms), ctypes.byref(by)))
+        return ms.value, by.value
 
     # ---- debug taps -------------------------------------------------------------------------
     def debug_run(self, left, right, last_stage: str):

@@ -116,6 +116,12 @@ int adc_last_stage_ms(const adc_engine* e, float out[6]);
 /* resolved configuration (wave_pairs, lanes, ...) */
 int adc_get_config(const adc_engine* e, adc_config* out);
 
+/* Times one kernel of the pipeline in isolation on the engine's own stream (CUDA events), over one
+ * wave of wave_pairs pairs: kernel_id 0 = cost volume, 1 = horizontal arm sum, 2 = vertical arm sum
+ * with division, 3 = scanline pass along x, 4 = scanline pass along y, 5 = WTA left+right.
+ * algorithmic_bytes (optional) receives the bytes one launch must move. */
+int adc_profile_kernel(adc_engine* e, int32_t kernel_id, int32_t reps, float* avg_ms, double* algorithmic_bytes);
+
 const char* adc_last_error(void);
 const char* adc_version(void);
 
