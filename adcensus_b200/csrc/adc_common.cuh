@@ -75,6 +75,7 @@ struct AdcWave {            // device pointers of one wave (S pairs)
     unsigned* so_rec;       // [S][N][rec words] per-pixel penalty records of the pass being run
     int* tile_stamp;        // [S][tiles] region voting: epoch of the last change near a 16x16 tile
     int* last_eval;         // [S][N]     region voting: epoch of a pixel's (or tile's) last evaluation
+    unsigned long long* wta_key;  // [S][N] right-view WTA keys (ordered cost << 32 | disparity index)
     uint8_t* vote_dq;       // [S][2][N]  region voting: rounded disparity index per pixel, NEW and OLD state
     const float* lut_ad;    // [766]  (1 - exp(-(s/3)/lambda_ad)) + 1, host libm expf
     const float* lut_cen;   // [64]   exp(-h/lambda_census)
@@ -95,7 +96,7 @@ size_t adc_so_bitrow_bytes(const AdcDims& dm);
 // one scanline pass: (sx,sy) in {(1,0),(-1,0),(0,1),(0,-1)}
 int adc_launch_scanline(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
                         cudaStream_t st, unsigned long long* launches);
-void adc_launch_wta(const AdcParams& P, const AdcWave& w, const float* vol, cudaStream_t st, unsigned long long* launches);
+int adc_launch_wta(const AdcParams& P, const AdcWave& w, const float* vol, cudaStream_t st, unsigned long long* launches);
 void adc_launch_outlier(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
 void adc_launch_build_lists(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
 void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);

@@ -124,6 +124,7 @@ size_t carve_lane(void* base, const AdcDims& dm, int S, AdcWave* w) {
     t.pend = c.take<int>((size_t)S * 2 * N);
     t.counters = c.take<int>((size_t)S * ADC_CNT);
     t.vote_dq = c.take<uint8_t>((size_t)S * 2 * N);
+    t.wta_key = c.take<unsigned long long>((size_t)S * N);
     t.rowcnt = c.take<int>((size_t)S * 2 * dm.H);
     t.so_bitrows = c.take<unsigned>((size_t)S * adc_so_bitrow_bytes(dm) / 4);
     t.so_rec = c.take<unsigned>((size_t)S * adc_so_rec_bytes(dm) / 4);
@@ -241,7 +242,7 @@ int enqueue_pipeline(adc_engine* e, Lane& ln, int nS, int last_stage, cudaEvent_
     if (ev) CK(cudaEventRecord(ev[3], st));
 
     // ---- stage 4: left + right disparity (ADCensusStereo.cpp:108-109)
-    adc_launch_wta(P, w, A, st, L);
+    if (adc_launch_wta(P, w, A, st, L)) return fail(ADC_ERR_UNSUPPORTED, "WTA launch failed");
     if (ev) CK(cudaEventRecord(ev[4], st));
     if (stop(ADC_STAGE_WTA)) return ADC_OK;
 
@@ -596,7 +597,7 @@ int adc_profile_kernel(adc_engine* e, int32_t kernel_id, int32_t reps, float* av
             case 2: adc_launch_arm_sum(P, w, w.volA, w.volB, 1, w.sup_h, ln.st, &e->launches); bytes = 2 * V + 6 * N; break;
             case 3: if (adc_launch_scanline(P, w, w.volA, w.volB, 1, 0, ln.st, &e->launches)) return fail(ADC_ERR_UNSUPPORTED, "scanline"); bytes = 2 * V + 6 * N; break;
             case 4: if (adc_launch_scanline(P, w, w.volA, w.volB, 0, 1, ln.st, &e->launches)) return fail(ADC_ERR_UNSUPPORTED, "scanline"); bytes = 2 * V + 6 * N; break;
-            case 5: adc_launch_wta(P, w, w.volA, ln.st, &e->launches); bytes = V + 8 * N; break;
+            case 5: if (adc_launch_wta(P, w, w.volA, ln.st, &e->launches)) return fail(ADC_ERR_UNSUPPORTED, "wta"); bytes = V + 8 * N; break;
             default: return fail(ADC_ERR_ARG, "adc_profile_kernel: unknown kernel id %d", kernel_id);
         }
     }

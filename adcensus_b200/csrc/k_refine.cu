@@ -7,6 +7,7 @@
 // answer.  Each kernel below is a parallel schedule that provably reproduces the sequential
 // result (argument given at each kernel); none of them approximates.
 #include "adc_common.cuh"
+#include <stdlib.h>
 
 // barrier over all threads of the thread-block cluster, with release/acquire ordering of memory
 __device__ __forceinline__ void cluster_sync_all() {
@@ -211,6 +212,14 @@ __device__ __forceinline__ void rv_stamp_tiles(int* tiles, int tw, int th, int x
 // because the CTAs sit on different SMs.
 #define RV_CLUSTER 8
 
+// USE_L1: read through L1 (plain loads).  The cluster barrier between rounds carries an acquire at
+// cluster scope, for which ptxas emits an L1 invalidate, so a round never sees lines cached before
+// the previous barrier; lines going stale *within* a round are harmless (asynchronous fixed point,
+// and the certifying round has no writes at all).
+template <bool USE_L1> __device__ __forceinline__ float rv_ld(const float* p) { return USE_L1 ? __ldca(p) : __ldcg(p); }
+template <bool USE_L1> __device__ __forceinline__ int rv_ld(const int* p) { return USE_L1 ? __ldca(p) : __ldcg(p); }
+
+template <bool USE_L1>
 __global__ void __cluster_dims__(RV_CLUSTER, 1, 1) __launch_bounds__(RV_THREADS)
 k_region_voting_global(AdcParams P, const uchar4* __restrict__ arms, float* disp_old, float* disp_new,
                        uint8_t* label, int* pend, int* counters, int* tile_stamp, int* last_eval) {
@@ -257,9 +266,9 @@ k_region_voting_global(AdcParams P, const uchar4* __restrict__ arms, float* disp
                 if (gtid == 0) __stcg(cnt + 4 + (rnd + 1) % 3, 0);  // flag of the NEXT round; nobody reads it now
                 bool warp_changed = false;
                 for (int idx = gwarp; idx < n; idx += n_gwarps) {
-                    const int p = __ldcg(list + idx);
+                    const int p = rv_ld<USE_L1>(list + idx);
                     const int y = p / W, x = p - y * W;
-                    if (__ldcg(tiles + (y / RV_TILE) * tw + x / RV_TILE) < __ldcg(evalep + p)) continue;  // inputs untouched since
+                    if (rv_ld<USE_L1>(tiles + (y / RV_TILE) * tw + x / RV_TILE) < rv_ld<USE_L1>(evalep + p)) continue;  // inputs untouched since
                     evals++;
                     for (int b = lane; b < D; b += 32) hist[b] = 0;
                     __syncwarp();
@@ -269,7 +278,7 @@ k_region_voting_global(AdcParams P, const uchar4* __restrict__ arms, float* disp
                         const uchar4 a2 = __ldg(A + rowi);
                         for (int s = -(int)a2.x + sub; s <= (int)a2.y; s += 8) {
                             const bool before = (t < 0) || (t == 0 && s < 0);
-                            const float d = before ? __ldcg(d_new + rowi + s) : __ldcg(d_old + rowi + s);
+                            const float d = before ? rv_ld<USE_L1>(d_new + rowi + s) : rv_ld<USE_L1>(d_old + rowi + s);
                             if (d != ADC_INVALID_F) {
                                 const int di = (int)roundf(d) - dm.dmin;  // lround: half away from zero
                                 if (di >= 0 && di < D) atomicAdd(&hist[di], 1);
@@ -517,7 +526,7 @@ k_region_voting_tiles(AdcParams P, const uchar4* __restrict__ arms, float* disp_
                         if (capped) __stcg(stamps + t, epoch);   // not yet locally consistent: look again next round
                     }
                 }
-                if (cta_changed && tid == 0) __stcg(cnt + 4 + rnd % 3, 1);
+                if (cta_changed && lane == 0) __stcg(cnt + 4 + rnd % 3, 1);   // every warp that saw a change
                 cluster_sync_all();
                 const int ch = __ldcg(cnt + 4 + rnd % 3);
                 rounds_total++;
@@ -561,7 +570,9 @@ k_region_voting_tiles(AdcParams P, const uchar4* __restrict__ arms, float* disp_
 void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
     // disp_l = committed state (OLD), disp_t = working copy (NEW); both hold the post-outlier map here
     const int reach = P.L1 > 0 ? P.L1 : 0;
-    if (P.dm.D <= 254 && reach <= RV_MAXREACH) {
+    static int mode = -1;   // development switch: 0 = shared-memory tiles, 1 = global via L1, 2 = global via L2
+    if (mode < 0) { const char* m = getenv("ADC_VOTE_MODE"); mode = m ? atoi(m) : 1; }
+    if (mode == 0 && P.dm.D <= 254 && reach <= RV_MAXREACH) {
         const int E = RV_T + 2 * reach;
         const size_t smem = (size_t)E * (E + 1) * 4 + (size_t)RV_WARPS * RV_MAXD * 4 + (size_t)RV_T * RV_T * 2;
         static bool attr_done = false;
@@ -575,8 +586,12 @@ void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, un
                                                                          w.pend, w.counters, w.tile_stamp, w.last_eval);
         *launches += 2;
     } else {
-        k_region_voting_global<<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.disp_l, w.disp_t, w.label, w.pend,
-                                                                        w.counters, w.tile_stamp, w.last_eval);
+        if (mode == 2)
+            k_region_voting_global<false><<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.disp_l, w.disp_t, w.label, w.pend,
+                                                                                   w.counters, w.tile_stamp, w.last_eval);
+        else
+            k_region_voting_global<true><<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.disp_l, w.disp_t, w.label, w.pend,
+                                                                                  w.counters, w.tile_stamp, w.last_eval);
         ++*launches;
     }
 }
@@ -737,7 +752,6 @@ void adc_launch_discontinuity(const AdcParams& P, const AdcWave& w, const float*
 //    neighbour is the thread's own previous result; the output goes to a second map.
 // =============================================================================================
 #define MED_THREADS 1024
-#define MED_ROWS 2   // rows per thread -> images up to 2048 rows
 
 __device__ __forceinline__ void cswap(float& a, float& b) { const float lo = fminf(a, b), hi = fmaxf(a, b); a = lo; b = hi; }
 
@@ -753,6 +767,9 @@ __device__ __forceinline__ float median9(float v[9]) {
     return v[4];
 }
 
+#define MED_PF 8   // wavefront steps between issuing a load and using it
+
+template <int MED_ROWS>   // rows per thread: 1 for H <= 1024, 2 up to 2048
 __global__ void __launch_bounds__(MED_THREADS)
 k_median_wavefront(AdcDims dm, const float* __restrict__ in, float* __restrict__ out) {
     extern __shared__ float med_ring[];   // [H][4] filtered values of each row, indexed by column & 3
@@ -762,62 +779,86 @@ k_median_wavefront(AdcDims dm, const float* __restrict__ in, float* __restrict__
     const int W = dm.W, H = dm.H;
     const float NINF = __int_as_float(0xff800000), PINF = ADC_INVALID_F;
     const int n_steps = W + 2 * H - 2;
-    float left_new[MED_ROWS];
+    // per row: a sliding window of ORIGINAL values of row y (columns x, x+1) and row y+1 (x-1, x, x+1),
+    // fed by a ring of loads issued MED_PF steps ahead (slot = step mod MED_PF, the same for every thread)
+    float A0[MED_ROWS], A1[MED_ROWS], Bm[MED_ROWS], B0[MED_ROWS], B1[MED_ROWS], left_new[MED_ROWS];
+    float ringA[MED_ROWS][MED_PF], ringB[MED_ROWS][MED_PF];
+    auto fetch = [&](int r, int t, float& a, float& b) {   // originals of column (t - 2y) + 2 for use at step t
+        const int y = threadIdx.x + r * MED_THREADS;
+        const int c = t - 2 * y + 2;
+        const bool ok = y < H && c >= 0 && c < W;
+        a = ok ? __ldg(src + y * W + c) : PINF;
+        b = (ok && y + 1 < H) ? __ldg(src + (y + 1) * W + c) : PINF;
+    };
 #pragma unroll
-    for (int r = 0; r < MED_ROWS; r++) left_new[r] = 0.f;
-    for (int t = 0; t < n_steps; t++) {
-        float res[MED_ROWS];
-        bool act[MED_ROWS];
+    for (int r = 0; r < MED_ROWS; r++) {
+        A0[r] = A1[r] = Bm[r] = B0[r] = B1[r] = PINF;
+        left_new[r] = PINF;
 #pragma unroll
-        for (int r = 0; r < MED_ROWS; r++) {
-            const int y = threadIdx.x + r * MED_THREADS;
-            const int x = t - 2 * y;
-            act[r] = y < H && x >= 0 && x < W;
-            res[r] = 0.f;
-            if (!act[r]) continue;
-            const bool up = y > 0, dn = y + 1 < H, lf = x > 0, rt = x + 1 < W;
-            float v[9];
-            const float* ring_up = med_ring + (size_t)(y - 1) * 4;
-            v[0] = (up && lf) ? ring_up[(x - 1) & 3] : PINF;
-            v[1] = up ? ring_up[x & 3] : PINF;
-            v[2] = (up && rt) ? ring_up[(x + 1) & 3] : PINF;
-            v[3] = lf ? left_new[r] : PINF;
-            v[4] = __ldg(src + y * W + x);
-            v[5] = rt ? __ldg(src + y * W + x + 1) : PINF;
-            v[6] = (dn && lf) ? __ldg(src + (y + 1) * W + x - 1) : PINF;
-            v[7] = dn ? __ldg(src + (y + 1) * W + x) : PINF;
-            v[8] = (dn && rt) ? __ldg(src + (y + 1) * W + x + 1) : PINF;
-            const int n = (1 + (int)up + (int)dn) * (1 + (int)lf + (int)rt);
-            // wanted rank n/2 of the n real values == rank 4 of 9 once (4 - n/2) of the absent slots
-            // hold -inf and the others +inf
-            int need = 4 - n / 2;
-            const bool present[9] = {up && lf, up, up && rt, lf, true, rt, dn && lf, dn, dn && rt};
+        for (int j = 0; j < MED_PF; j++) fetch(r, j - 2, ringA[r][j], ringB[r][j]);   // steps -2 .. MED_PF-3
+    }
+    // steps start at -2 so that columns 0 and 1 enter the window before the first real step
+    for (int tb = -2; tb < n_steps; tb += MED_PF) {
 #pragma unroll
-            for (int j = 0; j < 9; j++)
-                if (!present[j] && need > 0) { v[j] = NINF; need--; }
-            res[r] = median9(v);
+        for (int j = 0; j < MED_PF; j++) {
+            const int t = tb + j;
+            float res[MED_ROWS];
+            bool act[MED_ROWS];
+#pragma unroll
+            for (int r = 0; r < MED_ROWS; r++) {
+                const int y = threadIdx.x + r * MED_THREADS;
+                const int x = t - 2 * y;
+                // shift the window: it now holds columns x, x+1 (row y) and x-1, x, x+1 (row y+1)
+                A0[r] = A1[r]; A1[r] = ringA[r][j];
+                Bm[r] = B0[r]; B0[r] = B1[r]; B1[r] = ringB[r][j];
+                fetch(r, t + MED_PF, ringA[r][j], ringB[r][j]);
+                act[r] = t < n_steps && y < H && x >= 0 && x < W;
+                res[r] = 0.f;
+                if (!act[r]) continue;
+                const bool up = y > 0, dn = y + 1 < H, lf = x > 0, rt = x + 1 < W;
+                float v[9];
+                const float* ring_up = med_ring + (size_t)(y - 1) * 4;
+                v[0] = (up && lf) ? ring_up[(x - 1) & 3] : PINF;
+                v[1] = up ? ring_up[x & 3] : PINF;
+                v[2] = (up && rt) ? ring_up[(x + 1) & 3] : PINF;
+                v[3] = lf ? left_new[r] : PINF;
+                v[4] = A0[r];
+                v[5] = rt ? A1[r] : PINF;
+                v[6] = (dn && lf) ? Bm[r] : PINF;
+                v[7] = dn ? B0[r] : PINF;
+                v[8] = (dn && rt) ? B1[r] : PINF;
+                const int n = (1 + (int)up + (int)dn) * (1 + (int)lf + (int)rt);
+                // wanted rank n/2 of the n real values == rank 4 of 9 once (4 - n/2) of the absent slots
+                // hold -inf and the others +inf
+                int need = 4 - n / 2;
+                const bool present[9] = {up && lf, up, up && rt, lf, true, rt, dn && lf, dn, dn && rt};
+#pragma unroll
+                for (int q = 0; q < 9; q++)
+                    if (!present[q] && need > 0) { v[q] = NINF; need--; }
+                res[r] = median9(v);
+            }
+            // ring slot (x & 3) of row y holds column x-4, last read by row y+1 one step ago
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < MED_ROWS; r++) {
+                if (!act[r]) continue;
+                const int y = threadIdx.x + r * MED_THREADS;
+                const int x = t - 2 * y;
+                med_ring[(size_t)y * 4 + (x & 3)] = res[r];
+                left_new[r] = res[r];
+                dst[y * W + x] = res[r];
+            }
+            __syncthreads();
         }
-        // the ring slot (x & 3) of row y still holds column x-4, which row y+1 read for the last time
-        // at step t-1 (as its column (x-4)+1+... <= x-3): safe to overwrite after this step's reads
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < MED_ROWS; r++) {
-            if (!act[r]) continue;
-            const int y = threadIdx.x + r * MED_THREADS;
-            const int x = t - 2 * y;
-            med_ring[(size_t)y * 4 + (x & 3)] = res[r];
-            left_new[r] = res[r];
-            dst[y * W + x] = res[r];
-        }
-        __syncthreads();
     }
 }
 
 int adc_launch_median(const AdcParams& P, const AdcWave& w, const float* in, float* out, cudaStream_t st,
                       unsigned long long* launches) {
-    if (P.dm.H > MED_THREADS * MED_ROWS) return 1;
+    if (P.dm.H > MED_THREADS * 2) return 1;
     const size_t smem = (size_t)P.dm.H * 4 * sizeof(float);
-    k_median_wavefront<<<w.S, MED_THREADS, smem, st>>>(P.dm, in, out);
+    if (P.dm.H <= MED_THREADS) k_median_wavefront<1><<<w.S, MED_THREADS, smem, st>>>(P.dm, in, out);
+    else                       k_median_wavefront<2><<<w.S, MED_THREADS, smem, st>>>(P.dm, in, out);
     ++*launches;
     return 0;
 }

@@ -149,7 +149,14 @@ k_so_records(AdcDims dm, int tso, int sx, int sy, const uint8_t* __restrict__ dm
 }
 
 // ---------------------------------------------------------------------------------------------
+// The serial kernel.  A group of LPS lanes (8, 16 or 32) owns one scanline and keeps K = Dp/LPS
+// consecutive disparities per lane, so a warp advances 32/LPS neighbouring scanlines in lockstep.
+// Fewer lanes per line = more disparities per lane = the per-step bookkeeping (barriers, copy
+// issue, neighbour shuffles, the min butterfly) is amortised over more cost values; the kernel
+// was issue-bound with 2 values per lane.  For the +-y passes the lines of a warp are adjacent
+// columns, i.e. one contiguous 32/LPS * Dp * 4-byte run per step.
 #define SO_WARPS 4
+#define SO_PF 8      // steps of input kept in flight per line
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -159,43 +166,48 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-template <int K, int PF>
+template <int K, int LPS>
 __global__ void __launch_bounds__(SO_WARPS * 32)
 k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
            const unsigned* __restrict__ rec, int sx, int sy) {
+    constexpr int PF = SO_PF;
+    constexpr int LPW = 32 / LPS;               // lines per warp
     extern __shared__ __align__(16) unsigned char so_smem[];
     const AdcDims& dm = P.dm;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int line = blockIdx.x * SO_WARPS + wid;
+    const int sub = lane / LPS, gl = lane % LPS;   // line within the warp, lane within the line's group
+    const int line = (blockIdx.x * SO_WARPS + wid) * LPW + sub;
     const int pair = blockIdx.y;
     const int n_lines = sx ? dm.H : dm.W, n_steps = sx ? dm.W : dm.H;
-    if (line >= n_lines) return;   // whole warp; no block-level barriers are used below
+    const bool live = line < n_lines;            // dead groups run along (uniform control flow) but move no data
     const int W = dm.W, D = dm.D, Dp = dm.Dp;
-    const int pstep = sx + sy * W;  // signed pixel stride along the path
+    const int pstep = sx + sy * W;               // signed pixel stride along the path
     const int nrec = so_rec_words(Dp);
     const int cost_chunks = Dp >> 2, rec_chunks = nrec >> 2;      // 16-byte chunks per step
     const int slot_bytes = (Dp + nrec) * 4;
-    unsigned char* ring = so_smem + (size_t)wid * PF * slot_bytes;
+    unsigned char* ring = so_smem + (size_t)((wid * LPW + sub) * PF) * slot_bytes;
     const float* S = src + (size_t)pair * dm.vol_stride;
     float* O = dst + (size_t)pair * dm.vol_stride;
     const unsigned* R = rec + (size_t)pair * dm.N * nrec;
 
     const int x0 = sx ? (sx > 0 ? 0 : W - 1) : line;
     const int y0 = sy ? (sy > 0 ? 0 : dm.H - 1) : line;
-    int pi = y0 * W + x0;
+    long long pi = (long long)y0 * W + x0;
+    if (!live) pi = 0;
 
     auto prefetch = [&](int step) {   // issue the copies of `step` into its ring slot (no commit)
-        const long long p = (long long)(y0 * W + x0) + (long long)step * pstep;
+        if (!live) return;
+        const long long p = (long long)y0 * W + x0 + (long long)step * pstep;
         unsigned char* slot = ring + (size_t)(step % PF) * slot_bytes;
         const float* cs = S + (size_t)p * Dp;
-        for (int c = lane; c < cost_chunks; c += 32) cp_async16(slot + c * 16, cs + c * 4);
+        for (int c = gl; c < cost_chunks; c += LPS) cp_async16(slot + c * 16, cs + c * 4);
         const unsigned* rs = R + (size_t)p * nrec;
-        for (int c = lane; c < rec_chunks; c += 32) cp_async16(slot + Dp * 4 + c * 16, rs + c * 4);
+        for (int c = gl; c < rec_chunks; c += LPS) cp_async16(slot + Dp * 4 + c * 16, rs + c * 4);
     };
 
     bool valid[K];
 #pragma unroll
-    for (int k = 0; k < K; k++) valid[k] = (lane * K + k) < D;
+    for (int k = 0; k < K; k++) valid[k] = (gl * K + k) < D;
 
     // start the pipeline, then handle the path head: L = C  (scanline_optimizer.cpp:99-100)
 #pragma unroll
@@ -206,30 +218,29 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
     float L[K];
     {
         const float* head = S + (size_t)pi * Dp;
-        constexpr int G = Piece<K>::G, NP = Piece<K>::NP;
 #pragma unroll
-        for (int j = 0; j < NP; j++) {
-            const int d = lane * K + j * G;
-#pragma unroll
-            for (int g = 0; g < G; g++) L[j * G + g] = (d + g < Dp) ? __ldg(head + d + g) : 0.f;
+        for (int k = 0; k < K; k++) {
+            const int d = gl * K + k;
+            L[k] = (live && d < Dp) ? __ldg(head + d) : 0.f;
         }
     }
-    st_vec<K>(O + (size_t)pi * Dp, lane, Dp, L);
-    unsigned key = adc_f2key(ADC_LARGE_F);
+    if (live) st_vec<K>(O + (size_t)pi * Dp, gl, Dp, L);
+    float minL = ADC_LARGE_F;
 #pragma unroll
     for (int k = 0; k < K; k++) {
         if (!valid[k]) L[k] = ADC_LARGE_F;
-        key = min(key, adc_f2key(L[k]));
+        minL = fminf(minL, L[k]);
     }
-    float minL = adc_key2f(__reduce_min_sync(0xffffffffu, key));
+#pragma unroll
+    for (int o = LPS / 2; o >= 1; o >>= 1) minL = fminf(minL, __shfl_xor_sync(0xffffffffu, minL, o));
 
-    const int bit0 = lane * K;   // first disparity of this lane inside the record's bit string
+    const int bit0 = gl * K;   // first disparity of this lane inside the record's bit string
     for (int step = 1; step < n_steps; step++) {
         cp_async_wait<PF - 1>();     // the group of `step` has landed (for this lane's copies)
         __syncwarp();                // ... and for every other lane's
         const unsigned char* slot = ring + (size_t)(step % PF) * slot_bytes;
         float C[K];
-        ld_vec<K>(reinterpret_cast<const float*>(slot), lane, Dp, C);
+        ld_vec<K>(reinterpret_cast<const float*>(slot), gl, Dp, C);
         const unsigned* rw = reinterpret_cast<const unsigned*>(slot + Dp * 4);
         const bool a1 = rw[0] != 0u;
         const unsigned bits = __funnelshift_r(rw[1 + (bit0 >> 5)], rw[2 + (bit0 >> 5)], bit0 & 31);
@@ -238,49 +249,55 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
         cp_async_commit();
         pi += pstep;
 
-        const float up = __shfl_up_sync(0xffffffffu, L[K - 1], 1);
-        const float down = __shfl_down_sync(0xffffffffu, L[0], 1);
-        const float left_in = lane == 0 ? ADC_LARGE_F : up;
-        const float right_in = lane == 31 ? ADC_LARGE_F : down;
+        const float up = __shfl_up_sync(0xffffffffu, L[K - 1], 1, LPS);
+        const float down = __shfl_down_sync(0xffffffffu, L[0], 1, LPS);
+        const float left_in = gl == 0 ? ADC_LARGE_F : up;
+        const float right_in = gl == LPS - 1 ? ADC_LARGE_F : down;
+        // the three penalty classes of this pixel's left-image term (scanline_optimizer.cpp:129-141)
+        const float P1a = a1 ? P.p1 : P.p1_4, P1b = a1 ? P.p1_4 : P.p1_10;   // d2 < tso  /  d2 >= tso
+        const float P2a = a1 ? P.p2 : P.p2_4, P2b = a1 ? P.p2_4 : P.p2_10;
+        const float m4a = __fadd_rn(minL, P2a), m4b = __fadd_rn(minL, P2b);
 
         float Ln[K];
-        unsigned kmin = adc_f2key(ADC_LARGE_F);
+        float mn = ADC_LARGE_F;
 #pragma unroll
         for (int k = 0; k < K; k++) {
             const bool a2 = (bits >> k) & 1u;
-            const float P1 = (a1 && a2) ? P.p1 : ((a1 || a2) ? P.p1_4 : P.p1_10);   // :129-141
-            const float P2 = (a1 && a2) ? P.p2 : ((a1 || a2) ? P.p2_4 : P.p2_10);
+            const float P1 = a2 ? P1a : P1b;
             const float l1 = L[k];
             const float l2 = __fadd_rn(k > 0 ? L[k - 1] : left_in, P1);
             const float l3 = __fadd_rn(k < K - 1 ? L[k + 1] : right_in, P1);
-            const float l4 = __fadd_rn(minL, P2);
+            const float l4 = a2 ? m4a : m4b;
             float v = __fadd_rn(C[k], fminf(fminf(l1, l2), fminf(l3, l4)));
             v = __fmul_rn(v, 0.5f);
             Ln[k] = v;
-            if (valid[k]) kmin = min(kmin, adc_f2key(v));
+            if (valid[k]) mn = fminf(mn, v);
         }
-        st_vec<K>(O + (size_t)pi * Dp, lane, Dp, Ln);
+        if (live) st_vec<K>(O + (size_t)pi * Dp, gl, Dp, Ln);
 #pragma unroll
         for (int k = 0; k < K; k++) L[k] = valid[k] ? Ln[k] : ADC_LARGE_F;
-        minL = adc_key2f(__reduce_min_sync(0xffffffffu, kmin));
+#pragma unroll
+        for (int o = LPS / 2; o >= 1; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        minL = mn;
     }
     cp_async_wait<0>();
 }
 
-template <int K>
+template <int K, int LPS>
 static int launch_scanline_k(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
                              cudaStream_t st) {
-    constexpr int PF = 8;
+    constexpr int LPW = 32 / LPS;
     const int n_lines = sx ? P.dm.H : P.dm.W;
     const int slot_bytes = (P.dm.Dp + so_rec_words(P.dm.Dp)) * 4;
-    const size_t smem = (size_t)SO_WARPS * PF * slot_bytes;
+    const size_t smem = (size_t)SO_WARPS * LPW * SO_PF * slot_bytes;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_scanline<K, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(k_scanline<K, LPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_done = true;
     }
-    dim3 grid((n_lines + SO_WARPS - 1) / SO_WARPS, w.S);
-    k_scanline<K, PF><<<grid, SO_WARPS * 32, smem, st>>>(P, src, dst, w.so_rec, sx, sy);
+    const int lines_per_block = SO_WARPS * LPW;
+    dim3 grid((n_lines + lines_per_block - 1) / lines_per_block, w.S);
+    k_scanline<K, LPS><<<grid, SO_WARPS * 32, smem, st>>>(P, src, dst, w.so_rec, sx, sy);
     return 0;
 }
 
@@ -294,19 +311,19 @@ int adc_launch_scanline(const AdcParams& P, const AdcWave& w, const float* src, 
                         cudaStream_t st, unsigned long long* launches) {
     dim3 grid((P.dm.N + 255) / 256, w.S);
     k_so_records<<<grid, 256, 0, st>>>(P.dm, P.tso, sx, sy, w.dmap, w.so_bitrows, w.so_rec);
-    const int K = (P.dm.Dp + 31) / 32;
+    // lanes per line: as few as keep K = ceil(Dp / lanes) <= 8 (Dp is a multiple of 4)
+    const int Dp = P.dm.Dp;
     int rc = 1;
-    switch (K) {
-        case 1: rc = launch_scanline_k<1>(P, w, src, dst, sx, sy, st); break;
-        case 2: rc = launch_scanline_k<2>(P, w, src, dst, sx, sy, st); break;
-        case 3: rc = launch_scanline_k<3>(P, w, src, dst, sx, sy, st); break;
-        case 4: rc = launch_scanline_k<4>(P, w, src, dst, sx, sy, st); break;
-        case 5: rc = launch_scanline_k<5>(P, w, src, dst, sx, sy, st); break;
-        case 6: rc = launch_scanline_k<6>(P, w, src, dst, sx, sy, st); break;
-        case 7: rc = launch_scanline_k<7>(P, w, src, dst, sx, sy, st); break;
-        case 8: rc = launch_scanline_k<8>(P, w, src, dst, sx, sy, st); break;
-        default: return 1;  // D > 256 not supported by the warp-per-line kernel
-    }
+#define SO_GO(KK, LL) rc = launch_scanline_k<KK, LL>(P, w, src, dst, sx, sy, st)
+    if (Dp <= 64) {            // 8 lanes per line
+        switch ((Dp + 7) / 8) { case 1: SO_GO(1, 8); break; case 2: SO_GO(2, 8); break; case 3: SO_GO(3, 8); break; case 4: SO_GO(4, 8); break;
+                                case 5: SO_GO(5, 8); break; case 6: SO_GO(6, 8); break; case 7: SO_GO(7, 8); break; default: SO_GO(8, 8); }
+    } else if (Dp <= 128) {    // 16 lanes per line
+        switch ((Dp + 15) / 16) { case 5: SO_GO(5, 16); break; case 6: SO_GO(6, 16); break; case 7: SO_GO(7, 16); break; default: SO_GO(8, 16); }
+    } else if (Dp <= 256) {    // a whole warp per line
+        switch ((Dp + 31) / 32) { case 5: SO_GO(5, 32); break; case 6: SO_GO(6, 32); break; case 7: SO_GO(7, 32); break; default: SO_GO(8, 32); }
+    } else return 1;           // D > 256 not supported
+#undef SO_GO
     *launches += 2;
     return rc;
 }

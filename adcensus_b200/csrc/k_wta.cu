@@ -10,51 +10,93 @@ __device__ __forceinline__ float adc_subpixel(float c1, float c2, float cmin, in
     return (float)best;
 }
 
-// Left view: one thread per pixel scans its D costs (strict '>' so the first minimum wins).
-// Best at either end of the range -> Invalid_Float.
-__global__ void __launch_bounds__(128)
-k_wta_left(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l) {
-    const int pair = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= dm.N) return;
-    const float* v = vol + (size_t)pair * dm.vol_stride + (size_t)i * dm.Dp;
-    float best_cost = ADC_LARGE_F;
-    int best = 0;
-    const int Q = dm.Dp >> 2;
-    for (int q = 0; q < Q; q++) {
-        const float4 c = __ldg(reinterpret_cast<const float4*>(v) + q);
-        const float cc[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int di = 4 * q + j;
-            if (di < dm.D && best_cost > cc[j]) { best_cost = cc[j]; best = dm.dmin + di; }
-        }
-    }
-    float out;
-    if (best == dm.dmin || best == dm.dmax - 1) out = ADC_INVALID_F;
-    else out = adc_subpixel(__ldg(v + best - 1 - dm.dmin), __ldg(v + best + 1 - dm.dmin), best_cost, best);
-    disp_l[(size_t)pair * dm.N + i] = out;
+// One pass over the volume produces both views.  A CTA takes WT_PX pixels of one row; every thread
+// holds four consecutive costs of one pixel (one 128-bit load, the warp reads 512 contiguous bytes).
+//   left view : the pixel's minimum is a shared-memory atomicMin over 64-bit keys (ordered cost bits
+//               << 32 | disparity index), which is exactly "strict >, first minimum wins";
+//   right view: cost_R(xr, d) = cost_L(xr + d, d), so the same cost is also a candidate for right
+//               pixel x - d: a second atomicMin into a CTA-local array over the right pixels the CTA
+//               can touch, flushed with one global atomicMin per touched right pixel.
+// A small second kernel turns the right view's keys into disparities (two gathers for the parabola).
+#define WT_PX 64
+
+__device__ __forceinline__ unsigned long long wta_key(float c, int di) {
+    return ((unsigned long long)adc_f2key(c) << 32) | (unsigned)di;
 }
 
-// Right view: cost_R(x,d) = cost_L(x+d,d); columns outside the image are skipped for the minimum
-// but count as Large_Float for the parabola (:277-286); a best at either end of the range gives
-// the integer disparity, not Invalid (:290-293).  `best` starts at 0, not dmin, as in the reference.
-__global__ void __launch_bounds__(128)
-k_wta_right(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_r) {
+__global__ void __launch_bounds__(1024)
+k_wta_scan(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, unsigned long long* __restrict__ rkey) {
+    extern __shared__ unsigned long long wt_smem[];
+    const int pair = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * WT_PX;
+    const int Q = dm.Dp >> 2;
+    const int ppi = blockDim.x / Q;                  // pixels per inner iteration
+    const int span = WT_PX + dm.D - 1;
+    const int xr_base = x0 - (dm.dmax - 1);
+    unsigned long long* s_left = wt_smem;            // [ppi]
+    unsigned long long* s_right = wt_smem + ppi;     // [span]
+    const unsigned long long NONE = ~0ull;
+    for (int i = threadIdx.x; i < span; i += blockDim.x) s_right[i] = NONE;
+    const int p = threadIdx.x / Q, q = threadIdx.x - p * Q;
+    const float* rowv = vol + (size_t)pair * dm.vol_stride + (size_t)y * dm.W * dm.Dp;
+    for (int it = 0; it < WT_PX; it += ppi) {
+        if (threadIdx.x < ppi) s_left[threadIdx.x] = NONE;
+        __syncthreads();
+        const int x = x0 + it + p;
+        if (p < ppi && x < dm.W) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(rowv + (size_t)x * dm.Dp) + q);
+            const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+            unsigned long long best = NONE;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int di = 4 * q + j;
+                if (di < dm.D && cc[j] < ADC_LARGE_F) {          // min_cost starts at Large_Float, strict '>'
+                    const unsigned long long k = wta_key(cc[j], di);
+                    best = min(best, k);
+                    const int xr = x - (dm.dmin + di);
+                    if (xr >= 0 && xr < dm.W) atomicMin(&s_right[xr - xr_base], k);
+                }
+            }
+            if (best != NONE) atomicMin(&s_left[p], best);
+        }
+        __syncthreads();
+        if (threadIdx.x < ppi) {
+            const int xx = x0 + it + threadIdx.x;
+            if (xx < dm.W) {
+                const unsigned long long k = s_left[threadIdx.x];
+                float out = ADC_INVALID_F;
+                if (k != NONE) {
+                    const int di = (int)(unsigned)k, best = dm.dmin + di;
+                    if (best != dm.dmin && best != dm.dmax - 1) {   // ends of the range -> Invalid (ADCensusStereo.cpp:224-227)
+                        const float* v = rowv + (size_t)xx * dm.Dp;
+                        out = adc_subpixel(__ldg(v + di - 1), __ldg(v + di + 1), adc_key2f((unsigned)(k >> 32)), best);
+                    }
+                }
+                disp_l[(size_t)pair * dm.N + y * dm.W + xx] = out;
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < span; i += blockDim.x) {
+        const unsigned long long k = s_right[i];
+        if (k != NONE) atomicMin(rkey + (size_t)pair * dm.N + y * dm.W + xr_base + i, k);
+    }
+}
+
+// Right view finish: columns outside the image count as Large_Float for the parabola (:277-286); a
+// best at either end of the range gives the integer disparity, not Invalid (:290-293); `best` starts
+// at 0 (not dmin) when no column was valid, as in the reference.
+__global__ void __launch_bounds__(256)
+k_wta_right_finish(AdcDims dm, const float* __restrict__ vol, const unsigned long long* __restrict__ rkey,
+                   float* __restrict__ disp_r) {
     const int pair = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dm.N) return;
     const int y = i / dm.W, x = i - y * dm.W;
     const float* row = vol + (size_t)pair * dm.vol_stride + (size_t)y * dm.W * dm.Dp;
-    float best_cost = ADC_LARGE_F;
+    const unsigned long long k = rkey[(size_t)pair * dm.N + i];
     int best = 0;
-    for (int di = 0; di < dm.D; di++) {
-        const int xl = x + dm.dmin + di;
-        if (xl >= 0 && xl < dm.W) {
-            const float c = __ldg(row + (size_t)xl * dm.Dp + di);
-            if (best_cost > c) { best_cost = c; best = dm.dmin + di; }
-        }
-    }
+    float best_cost = ADC_LARGE_F;
+    if (k != ~0ull) { best = dm.dmin + (int)(unsigned)k; best_cost = adc_key2f((unsigned)(k >> 32)); }
     float out = (float)best;
     const int i1 = best - 1 - dm.dmin, i2 = best + 1 - dm.dmin;
     if (best != dm.dmin && best != dm.dmax - 1 && i1 >= 0 && i2 < dm.D) {
@@ -66,9 +108,19 @@ k_wta_right(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_
     disp_r[(size_t)pair * dm.N + i] = out;
 }
 
-void adc_launch_wta(const AdcParams& P, const AdcWave& w, const float* vol, cudaStream_t st, unsigned long long* launches) {
-    dim3 grid((P.dm.N + 127) / 128, w.S);
-    k_wta_left<<<grid, 128, 0, st>>>(P.dm, vol, w.disp_l);
-    k_wta_right<<<grid, 128, 0, st>>>(P.dm, vol, w.disp_r);
+int adc_launch_wta(const AdcParams& P, const AdcWave& w, const float* vol, cudaStream_t st, unsigned long long* launches) {
+    const int Q = P.dm.Dp / 4;
+    int ppi = 1024 / Q;
+    if (ppi > WT_PX) ppi = WT_PX;
+    if (ppi < 1) return 1;
+    while (WT_PX % ppi) ppi--;                       // WT_PX is a power of two; keeps the iteration count whole
+    const int threads = ppi * Q;
+    const size_t smem = (size_t)(ppi + WT_PX + P.dm.D - 1) * sizeof(unsigned long long);
+    if (cudaMemsetAsync(w.wta_key, 0xff, (size_t)w.S * P.dm.N * sizeof(unsigned long long), st) != cudaSuccess) return 1;
+    dim3 grid((P.dm.W + WT_PX - 1) / WT_PX, P.dm.H, w.S);
+    k_wta_scan<<<grid, threads, smem, st>>>(P.dm, vol, w.disp_l, w.wta_key);
+    dim3 grid2((P.dm.N + 255) / 256, w.S);
+    k_wta_right_finish<<<grid2, 256, 0, st>>>(P.dm, vol, w.wta_key, w.disp_r);
     *launches += 2;
+    return 0;
 }

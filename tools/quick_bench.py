@@ -1,5 +1,5 @@
 """Rough device-resident throughput of the Cone batch (development aid, not the contract bench)."""
-import sys, time
+import os, sys, time
 from pathlib import Path
 import numpy as np
 import torch
@@ -11,11 +11,12 @@ import adc_testlib as T
 left, right = T.load_cone()
 h, w, _ = left.shape
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-for S, lanes in ((16, 3), (8, 3), (16, 2), (32, 2)):
+cfgs = [tuple(int(v) for v in c.split("x")) for c in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["16x3", "8x3", "32x2"])]
+dl = torch.from_numpy(np.repeat(left[None], n, 0)).cuda()
+dr = torch.from_numpy(np.repeat(right[None], n, 0)).cuda()
+dd = torch.empty((n, h, w), dtype=torch.float32, device="cuda")
+for S, lanes in cfgs:
     eng = A.Engine(w, h, A.ADCensusOption(), wave_pairs=S, lanes=lanes)
-    dl = torch.from_numpy(np.repeat(left[None], n, 0)).cuda()
-    dr = torch.from_numpy(np.repeat(right[None], n, 0)).cuda()
-    dd = torch.empty((n, h, w), dtype=torch.float32, device="cuda")
     st = torch.cuda.current_stream()
     for _ in range(2):
         eng.match_batch_device(n, dl.data_ptr(), dr.data_ptr(), dd.data_ptr(), st.cuda_stream)
@@ -28,9 +29,12 @@ for S, lanes in ((16, 3), (8, 3), (16, 2), (32, 2)):
     e1.record(st)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    print(f"S={S} lanes={lanes}: {n} pairs in {ms:.2f} ms -> {n / ms * 1000:.1f} maps/s", flush=True)
+    print(f"vote_mode={os.environ.get('ADC_VOTE_MODE','-')} S={S} lanes={lanes}: {n} pairs in {ms:.2f} ms -> {n / ms * 1000:.1f} maps/s", flush=True)
+    if (S, lanes) == cfgs[0]:
+        for name in ("cost_volume", "arm_sum_h", "arm_sum_v_div", "scanline_x", "scanline_y", "wta"):
+            kms, kb = eng.profile_kernel(name, 5)
+            print(f"   kernel {name:14s} {kms*1000:8.1f} us per wave of {S}  -> {kb/kms/1e6:8.1f} GB/s algorithmic")
     eng.close()
-# per-stage times of a single Match
 eng = A.Engine(w, h, A.ADCensusOption())
 for _ in range(3):
     d = eng.match(left, right)
