@@ -69,122 +69,98 @@ void adc_launch_gray_census(const AdcParams& P, const AdcWave& w, cudaStream_t s
 // (sum of abs differences 0..765, Hamming 0..63): they come from tables built on the host with the
 // host's libm expf, evaluated in the reference's order  ((1 - e_ad) + 1) - e_cen
 // (cost_computor.cpp:110-117), so the volume is bit-identical to the CPU path by construction.
+//
+// One CTA walks a whole image row in chunks of `ppc` pixels.  Per chunk the right-image span the
+// chunk can match is staged in shared memory as packed BGR words + census words, split into four
+// arrays by (index mod 4) so that the stride-4 walk of a thread quad is conflict-free.  The tables
+// are staged once per CTA, replicated (x32 for the 64-entry census table, x8 for the 766-entry AD
+// table) so that the data-dependent lookups of a warp spread over the banks: the first two versions
+// of this kernel were bound by L1 / shared-memory bank conflicts on exactly these gathers.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_cost_volume_direct(AdcDims dm, int px_per_block, const uint8_t* __restrict__ bgr,
-              const unsigned long long* __restrict__ census, float* __restrict__ vol,
-              const float* __restrict__ lut_ad, const float* __restrict__ lut_cen) {
-    const int pair = blockIdx.z;
-    const int y = blockIdx.y;
-    const int Q = dm.Dp >> 2;
-    const int p = threadIdx.x / Q, q = threadIdx.x - p * Q;
-    const int x = blockIdx.x * px_per_block + p;
-    if (p >= px_per_block || x >= dm.W) return;
-    const uint8_t* left = bgr + (size_t)pair * 2 * dm.N * 3;
-    const uint8_t* right = left + (size_t)dm.N * 3;
-    const unsigned long long* cen_l = census + (size_t)pair * 2 * dm.N;
-    const unsigned long long* cen_r = cen_l + dm.N;
-    const int row = y * dm.W;
-    const uchar3 cl = adc_load_bgr(left, row + x);
-    const unsigned long long bl = __ldg(cen_l + row + x);
-    float out[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int di = 4 * q + j;
-        const int xr = x - (dm.dmin + di);
-        float c = 1.0f;  // out-of-image match: cost_computor.cpp:101-104
-        if (di >= dm.D) c = 0.0f;  // padding lane, never read as a cost
-        else if (xr >= 0 && xr < dm.W) {
-            const uchar3 cr = adc_load_bgr(right, row + xr);
-            const int sad = abs((int)cl.x - (int)cr.x) + abs((int)cl.y - (int)cr.y) + abs((int)cl.z - (int)cr.z);
-            const int ham = __popcll(bl ^ __ldg(cen_r + row + xr));
-            c = __fsub_rn(__ldg(lut_ad + sad), __ldg(lut_cen + ham));
-        }
-        out[j] = c;
-    }
-    float4* dst = reinterpret_cast<float4*>(vol + (size_t)pair * dm.vol_stride + ((size_t)row + x) * dm.Dp) + q;
-    *dst = make_float4(out[0], out[1], out[2], out[3]);
-}
-
-#define CV_PX 32   // pixels of one row per CTA
+#define CV_AD_REP 8
 
 __global__ void __launch_bounds__(1024)
-k_cost_volume(AdcDims dm, const uint8_t* __restrict__ bgr,
+k_cost_volume(AdcDims dm, int ppc, const uint8_t* __restrict__ bgr,
               const unsigned long long* __restrict__ census, float* __restrict__ vol,
               const float* __restrict__ lut_ad, const float* __restrict__ lut_cen) {
-    // One CTA = CV_PX pixels of one row x all disparities.  The right-image span they can match
-    // ([x0-dmax+1, x0+CV_PX-1-dmin]) is staged once in shared memory as packed BGR words + census
-    // words, together with the two exp() tables, so the inner loop is four shared-memory reads per
-    // cost instead of seven global ones (the first version was L1-issue-bound at 95%).
     extern __shared__ __align__(16) unsigned char cv_smem[];
-    const int pair = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * CV_PX;
+    const int pair = blockIdx.y, y = blockIdx.x;
     const int Q = dm.Dp >> 2;                       // threads per pixel
-    const int span = CV_PX + dm.D - 1;              // right pixels staged
-    const int xr_base = x0 - (dm.dmax - 1);         // image column of staged entry 0
-    unsigned long long* s_cen = reinterpret_cast<unsigned long long*>(cv_smem);          // [span]
-    unsigned* s_bgr = reinterpret_cast<unsigned*>(s_cen + span);                          // [span]
-    float* s_ad = reinterpret_cast<float*>(s_bgr + span);                                 // [766]
-    float* s_ce = s_ad + 766;                                                             // [64]
+    const int span = ppc + dm.D - 1;                // right pixels staged per chunk
+    const int sq = (span + 3) / 4 + 1;              // entries per residue array (padded)
+    float* s_ce = reinterpret_cast<float*>(cv_smem);                                      // [64][32]
+    float* s_ad = s_ce + 64 * 32;                                                         // [766][CV_AD_REP]
+    unsigned long long* s_cen = reinterpret_cast<unsigned long long*>(s_ad + 766 * CV_AD_REP);  // [4][sq]
+    unsigned* s_bgr = reinterpret_cast<unsigned*>(s_cen + 4 * sq);                        // [4][sq]
     const uint8_t* left = bgr + (size_t)pair * 2 * dm.N * 3;
     const uint8_t* right = left + (size_t)dm.N * 3;
     const unsigned long long* cen_l = census + (size_t)pair * 2 * dm.N;
     const unsigned long long* cen_r = cen_l + dm.N;
     const int row = y * dm.W;
-    for (int i = threadIdx.x; i < span; i += blockDim.x) {
-        const int xr = xr_base + i;
-        unsigned long long c = 0ull;
-        unsigned pix = 0xffffffffu;                 // marker: outside the image
-        if (xr >= 0 && xr < dm.W) {
-            c = __ldg(cen_r + row + xr);
-            const uchar3 v = adc_load_bgr(right, row + xr);
-            pix = (unsigned)v.x | ((unsigned)v.y << 8) | ((unsigned)v.z << 16);
-        }
-        s_cen[i] = c;
-        s_bgr[i] = pix;
-    }
-    for (int i = threadIdx.x; i < 766; i += blockDim.x) s_ad[i] = __ldg(lut_ad + i);
-    if (threadIdx.x < 64) s_ce[threadIdx.x] = __ldg(lut_cen + threadIdx.x);
-    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) s_ce[i] = __ldg(lut_cen + (i >> 5));
+    for (int i = threadIdx.x; i < 766 * CV_AD_REP; i += blockDim.x) s_ad[i] = __ldg(lut_ad + i / CV_AD_REP);
     const int p = threadIdx.x / Q, q = threadIdx.x - p * Q;
-    const int x = x0 + p;
-    if (p >= CV_PX || x >= dm.W) return;
-    const uchar3 cl = adc_load_bgr(left, row + x);
-    const unsigned long long bl = __ldg(cen_l + row + x);
-    float* out = vol + (size_t)pair * dm.vol_stride + ((size_t)row + x) * dm.Dp;
-    // disparities q, q+Q, q+2Q, q+3Q: neighbouring threads read neighbouring staged entries (no bank
-    // conflicts) and write neighbouring floats (full 32-byte sectors)
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int di = q + j * Q;
-        float c = 1.0f;                             // out-of-image match: cost_computor.cpp:101-104
-        if (di >= dm.D) c = 0.0f;                   // padding lane, never read as a cost
-        else {
-            const int i = (x - (dm.dmin + di)) - xr_base;
-            const unsigned pix = s_bgr[i];
-            if (pix != 0xffffffffu) {
-                const int sad = abs((int)cl.x - (int)(pix & 255u)) + abs((int)cl.y - (int)((pix >> 8) & 255u)) +
-                                abs((int)cl.z - (int)((pix >> 16) & 255u));
-                const int ham = __popcll(bl ^ s_cen[i]);
-                c = __fsub_rn(s_ad[sad], s_ce[ham]);
+    for (int x0 = 0; x0 < dm.W; x0 += ppc) {
+        const int xr_base = x0 - (dm.dmax - 1);     // image column of staged entry 0
+        __syncthreads();                            // previous chunk fully consumed (and tables visible)
+        for (int i = threadIdx.x; i < span; i += blockDim.x) {
+            const int xr = xr_base + i;
+            unsigned long long c = 0ull;
+            unsigned pix = 0xffffffffu;             // marker: outside the image
+            if (xr >= 0 && xr < dm.W) {
+                c = __ldg(cen_r + row + xr);
+                const uchar3 v = adc_load_bgr(right, row + xr);
+                pix = (unsigned)v.x | ((unsigned)v.y << 8) | ((unsigned)v.z << 16);
             }
+            s_cen[(i & 3) * sq + (i >> 2)] = c;
+            s_bgr[(i & 3) * sq + (i >> 2)] = pix;
         }
-        out[di] = c;
+        __syncthreads();
+        const int x = x0 + p;
+        if (p < ppc && x < dm.W) {
+            const uchar3 cl = adc_load_bgr(left, row + x);
+            const unsigned long long bl = __ldg(cen_l + row + x);
+            float out[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int di = 4 * q + j;
+                float c = 1.0f;                     // out-of-image match: cost_computor.cpp:101-104
+                if (di >= dm.D) c = 0.0f;           // padding lane, never read as a cost
+                else {
+                    const int i = (x - (dm.dmin + di)) - xr_base;
+                    const int si = (i & 3) * sq + (i >> 2);
+                    const unsigned pix = s_bgr[si];
+                    if (pix != 0xffffffffu) {
+                        const int sad = abs((int)cl.x - (int)(pix & 255u)) + abs((int)cl.y - (int)((pix >> 8) & 255u)) +
+                                        abs((int)cl.z - (int)((pix >> 16) & 255u));
+                        const int ham = __popcll(bl ^ s_cen[si]);
+                        c = __fsub_rn(s_ad[sad * CV_AD_REP + (lane & (CV_AD_REP - 1))], s_ce[ham * 32 + lane]);
+                    }
+                }
+                out[j] = c;
+            }
+            float4* dst = reinterpret_cast<float4*>(vol + (size_t)pair * dm.vol_stride + ((size_t)row + x) * dm.Dp) + q;
+            *dst = make_float4(out[0], out[1], out[2], out[3]);
+        }
     }
 }
 
 void adc_launch_cost(const AdcParams& P, const AdcWave& w, float* vol, cudaStream_t st, unsigned long long* launches) {
     const int Q = P.dm.Dp / 4;
-    const int threads = CV_PX * Q;                  // D <= 128 -> <= 1024 threads
-    if (threads <= 1024) {
-        const size_t smem = (size_t)(CV_PX + P.dm.D - 1) * 12 + (766 + 64) * 4;
-        dim3 grid((P.dm.W + CV_PX - 1) / CV_PX, P.dm.H, w.S);
-        k_cost_volume<<<grid, threads, smem, st>>>(P.dm, w.bgr, w.census, vol, w.lut_ad, w.lut_cen);
-    } else {
-        int ppb = 256 / Q;
-        if (ppb < 1) ppb = 1;
-        dim3 grid((P.dm.W + ppb - 1) / ppb, P.dm.H, w.S);
-        k_cost_volume_direct<<<grid, ppb * Q, 0, st>>>(P.dm, ppb, w.bgr, w.census, vol, w.lut_ad, w.lut_cen);
+    int ppc = 1024 / Q;
+    if (ppc > 32) ppc = 32;
+    if (ppc < 1) ppc = 1;
+    const int threads = ppc * Q;
+    const int span = ppc + P.dm.D - 1, sq = (span + 3) / 4 + 1;
+    const size_t smem = (size_t)(64 * 32 + 766 * CV_AD_REP) * 4 + (size_t)4 * sq * 12;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_cost_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_done = true;
     }
+    dim3 grid(P.dm.H, w.S);
+    k_cost_volume<<<grid, threads, smem, st>>>(P.dm, ppc, w.bgr, w.census, vol, w.lut_ad, w.lut_cen);
     ++*launches;
 }
 

@@ -273,12 +273,16 @@ k_region_voting_global(AdcParams P, const uchar4* __restrict__ arms, float* disp
                     for (int b = lane; b < D; b += 32) hist[b] = 0;
                     __syncwarp();
                     const uchar4 a = __ldg(A + p);
-                    for (int t = -(int)a.z + grp; t <= (int)a.w; t += 4) {
+                    // one region row per lane: the arm loads of all rows go out together, then every lane
+                    // streams its own row segment (independent loads, several in flight)
+                    for (int t = -(int)a.z + lane; t <= (int)a.w; t += 32) {
                         const int rowi = (y + t) * W + x;
                         const uchar4 a2 = __ldg(A + rowi);
-                        for (int s = -(int)a2.x + sub; s <= (int)a2.y; s += 8) {
-                            const bool before = (t < 0) || (t == 0 && s < 0);
-                            const float d = before ? rv_ld<USE_L1>(d_new + rowi + s) : rv_ld<USE_L1>(d_old + rowi + s);
+                        const int s_lo = -(int)a2.x, s_hi = (int)a2.y;
+                        const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);   // first s that reads OLD
+#pragma unroll 4
+                        for (int s = s_lo; s <= s_hi; s++) {
+                            const float d = s < s_mid ? rv_ld<USE_L1>(d_new + rowi + s) : rv_ld<USE_L1>(d_old + rowi + s);
                             if (d != ADC_INVALID_F) {
                                 const int di = (int)roundf(d) - dm.dmin;  // lround: half away from zero
                                 if (di >= 0 && di < D) atomicAdd(&hist[di], 1);
@@ -783,9 +787,9 @@ k_median_wavefront(AdcDims dm, const float* __restrict__ in, float* __restrict__
     // fed by a ring of loads issued MED_PF steps ahead (slot = step mod MED_PF, the same for every thread)
     float A0[MED_ROWS], A1[MED_ROWS], Bm[MED_ROWS], B0[MED_ROWS], B1[MED_ROWS], left_new[MED_ROWS];
     float ringA[MED_ROWS][MED_PF], ringB[MED_ROWS][MED_PF];
-    auto fetch = [&](int r, int t, float& a, float& b) {   // originals of column (t - 2y) + 2 for use at step t
+    auto fetch = [&](int r, int t, float& a, float& b) {   // originals of column x + 1 = (t - 2y) + 1, consumed at step t
         const int y = threadIdx.x + r * MED_THREADS;
-        const int c = t - 2 * y + 2;
+        const int c = t - 2 * y + 1;
         const bool ok = y < H && c >= 0 && c < W;
         a = ok ? __ldg(src + y * W + c) : PINF;
         b = (ok && y + 1 < H) ? __ldg(src + (y + 1) * W + c) : PINF;
@@ -797,7 +801,7 @@ k_median_wavefront(AdcDims dm, const float* __restrict__ in, float* __restrict__
 #pragma unroll
         for (int j = 0; j < MED_PF; j++) fetch(r, j - 2, ringA[r][j], ringB[r][j]);   // steps -2 .. MED_PF-3
     }
-    // steps start at -2 so that columns 0 and 1 enter the window before the first real step
+    // steps start early so that column 0 enters the window (at x = -1) before the first real step
     for (int tb = -2; tb < n_steps; tb += MED_PF) {
 #pragma unroll
         for (int j = 0; j < MED_PF; j++) {

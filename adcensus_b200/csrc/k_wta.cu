@@ -108,7 +108,89 @@ k_wta_right_finish(AdcDims dm, const float* __restrict__ vol, const unsigned lon
     disp_r[(size_t)pair * dm.N + i] = out;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast path (Dp <= 192): no atomics.  A CTA stages the costs of WT_PX + D - 1 neighbouring columns of
+// one row in shared memory (coalesced 128-bit loads, row stride Dp+1 words so that both scans below
+// are bank-conflict free), then one thread per pixel scans d = 0..D-1 sequentially -- for the left
+// view down its own column vector, for the right view along the diagonal cost_L(xr + d, d) -- with
+// the reference's strict '>' comparison.  The halo columns are read twice (second time from L2).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(2 * WT_PX)
+k_wta_tile(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, float* __restrict__ disp_r) {
+    extern __shared__ float wt_tile[];
+    const int pair = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * WT_PX;
+    const int Q = dm.Dp >> 2, DS = dm.Dp + 1;
+    const int col_lo = x0 + min(0, dm.dmin);
+    const int col_hi = x0 + WT_PX - 1 + max(0, dm.dmax - 1);
+    const int ncols = col_hi - col_lo + 1;
+    const float* rowv = vol + (size_t)pair * dm.vol_stride + (size_t)y * dm.W * dm.Dp;
+    for (int i = threadIdx.x; i < ncols * Q; i += blockDim.x) {
+        const int c = i / Q, q = i - c * Q;
+        const int x = col_lo + c;
+        if (x >= 0 && x < dm.W) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(rowv + (size_t)x * dm.Dp) + q);
+            float* t = wt_tile + c * DS + 4 * q;
+            t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+        }
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < WT_PX) {                                   // ---- left view (ADCensusStereo.cpp:188-243)
+        const int x = x0 + t;
+        if (x < dm.W) {
+            const float* v = wt_tile + (x - col_lo) * DS;
+            float best_cost = ADC_LARGE_F;
+            int best = 0;
+            for (int di = 0; di < dm.D; di++) {
+                const float c = v[di];
+                if (best_cost > c) { best_cost = c; best = dm.dmin + di; }
+            }
+            float out = ADC_INVALID_F;
+            const int i1 = best - 1 - dm.dmin, i2 = best + 1 - dm.dmin;
+            if (best != dm.dmin && best != dm.dmax - 1 && i1 >= 0 && i2 < dm.D)
+                out = adc_subpixel(v[i1], v[i2], best_cost, best);
+            disp_l[(size_t)pair * dm.N + y * dm.W + x] = out;
+        }
+    } else {                                           // ---- right view (ADCensusStereo.cpp:245-310)
+        const int x = x0 + t - WT_PX;
+        if (x < dm.W) {
+            float best_cost = ADC_LARGE_F;
+            int best = 0;
+            for (int di = 0; di < dm.D; di++) {
+                const int xl = x + dm.dmin + di;
+                if (xl >= 0 && xl < dm.W) {
+                    const float c = wt_tile[(xl - col_lo) * DS + di];
+                    if (best_cost > c) { best_cost = c; best = dm.dmin + di; }
+                }
+            }
+            float out = (float)best;
+            const int i1 = best - 1 - dm.dmin, i2 = best + 1 - dm.dmin;
+            if (best != dm.dmin && best != dm.dmax - 1 && i1 >= 0 && i2 < dm.D) {
+                const int x1 = x + best - 1, x2 = x + best + 1;
+                const float c1 = (x1 >= 0 && x1 < dm.W) ? wt_tile[(x1 - col_lo) * DS + i1] : ADC_LARGE_F;
+                const float c2 = (x2 >= 0 && x2 < dm.W) ? wt_tile[(x2 - col_lo) * DS + i2] : ADC_LARGE_F;
+                out = adc_subpixel(c1, c2, best_cost, best);
+            }
+            disp_r[(size_t)pair * dm.N + y * dm.W + x] = out;
+        }
+    }
+}
+
 int adc_launch_wta(const AdcParams& P, const AdcWave& w, const float* vol, cudaStream_t st, unsigned long long* launches) {
+    const int ncols = WT_PX + (P.dm.dmax - 1 > 0 ? P.dm.dmax - 1 : 0) - (P.dm.dmin < 0 ? P.dm.dmin : 0);
+    const size_t tile_bytes = (size_t)ncols * (P.dm.Dp + 1) * sizeof(float);
+    if (tile_bytes <= 200 * 1024) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(k_wta_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_done = true;
+        }
+        dim3 grid((P.dm.W + WT_PX - 1) / WT_PX, P.dm.H, w.S);
+        k_wta_tile<<<grid, 2 * WT_PX, tile_bytes, st>>>(P.dm, vol, w.disp_l, w.disp_r);
+        ++*launches;
+        return 0;
+    }
+    // wide disparity ranges: atomic-key version
     const int Q = P.dm.Dp / 4;
     int ppi = 1024 / Q;
     if (ppi > WT_PX) ppi = WT_PX;

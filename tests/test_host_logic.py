@@ -86,6 +86,20 @@ def test_product_never_touches_the_oracle():
             assert "adc_oracle" not in txt and "adc_testlib" not in txt and "libadcensus_ref" not in txt, f
 
 
+def test_reference_style_cpp_caller_compiles_and_links(tmp_path):
+    """A C++ program written against the reference's class interface builds against include/ and
+    the shared library, and sees the reference's error truth table."""
+    A, L = _lib()
+    exe = tmp_path / "dropin"
+    r = subprocess.run(["g++", "-std=c++17", str(ROOT / "tests" / "cpp" / "dropin_main.cpp"), f"-I{ROOT / 'include'}",
+                        f"-L{A.lib_path().parent}", "-ladcensus_b200", f"-Wl,-rpath,{A.lib_path().parent}", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    run = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, ADC_B200_QUIET="1"))
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert "DROPIN_OK" in run.stdout or "DROPIN_NO_GPU" in run.stdout
+
+
 def test_shard_bounds():
     from adcensus_b200.parallel import shard_bounds
     assert shard_bounds(4096, 8) == [(i * 512, (i + 1) * 512) for i in range(8)]

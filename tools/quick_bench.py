@@ -35,6 +35,17 @@ for S, lanes in cfgs:
             kms, kb = eng.profile_kernel(name, 5)
             print(f"   kernel {name:14s} {kms*1000:8.1f} us per wave of {S}  -> {kb/kms/1e6:8.1f} GB/s algorithmic")
     eng.close()
+if os.environ.get("ADC_SWEEP_S"):
+    for S in (1, 2, 4, 8):
+        eng = A.Engine(w, h, A.ADCensusOption(), wave_pairs=S, lanes=1)
+        eng.match_batch_device(S, dl.data_ptr(), dr.data_ptr(), dd.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        line = f"S={S}: per-pair us:"
+        for name in ("cost_volume", "arm_sum_h", "arm_sum_v_div", "scanline_x", "scanline_y", "wta"):
+            kms, kb = eng.profile_kernel(name, 10)
+            line += f" {name}={kms*1000/S:.1f}"
+        print(line, flush=True)
+        eng.close()
 eng = A.Engine(w, h, A.ADCensusOption())
 for _ in range(3):
     d = eng.match(left, right)
