@@ -76,6 +76,7 @@ struct AdcWave {            // device pointers of one wave (S pairs)
     int* tile_stamp;        // [S][tiles] region voting: epoch of the last change near a 16x16 tile
     int* last_eval;         // [S][N]     region voting: epoch of a pixel's (or tile's) last evaluation
     unsigned long long* wta_key;  // [S][N] right-view WTA keys (ordered cost << 32 | disparity index)
+    uchar2* vote_alr;       // [S][N]     region voting: horizontal arms only (left, right)
     uint8_t* vote_dq;       // [S][2][N]  region voting: rounded disparity index per pixel, NEW and OLD state
     const float* lut_ad;    // [766]  (1 - exp(-(s/3)/lambda_ad)) + 1, host libm expf
     const float* lut_cen;   // [64]   exp(-h/lambda_census)

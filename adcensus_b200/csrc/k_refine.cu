@@ -362,7 +362,8 @@ k_region_voting_global(AdcParams P, const uchar4* __restrict__ arms, float* disp
 #define RV_MAXREACH 34
 #define RV_INNER 4
 
-__global__ void k_vote_encode(AdcDims dm, const float* __restrict__ disp, uint8_t* __restrict__ dq) {
+__global__ void k_vote_encode(AdcDims dm, const float* __restrict__ disp, const uchar4* __restrict__ arms,
+                              uint8_t* __restrict__ dq, uchar2* __restrict__ alr) {
     const int pair = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dm.N) return;
@@ -374,6 +375,147 @@ __global__ void k_vote_encode(AdcDims dm, const float* __restrict__ disp, uint8_
     }
     dq[((size_t)pair * 2 + 0) * dm.N + i] = v;
     dq[((size_t)pair * 2 + 1) * dm.N + i] = v;
+    const uchar4 a = arms[(size_t)pair * dm.N + i];
+    alr[(size_t)pair * dm.N + i] = make_uchar2(a.x, a.y);   // horizontal arms, 2 bytes per pixel
+}
+
+// ---------------------------------------------------------------------------------------------
+// Byte-state version of the balanced cluster kernel (default).  Same algorithm as
+// k_region_voting_global, but the working set of a round -- the +-reach rows around the pixels being
+// evaluated -- is 4 bytes per pixel (NEW byte, OLD byte, left/right arm bytes) instead of 12, so it
+// fits the L1 of every SM of the cluster and the dependent loads of an evaluation hit L1 instead of
+// making an L2 round trip each.  Loads are ld.global.ca; the cluster barrier's acquire plus a
+// __threadfence() (CCTL.IVALL) between rounds drop stale lines.
+// ---------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(RV_CLUSTER, 1, 1) __launch_bounds__(RV_THREADS)
+k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restrict__ alr_all,
+                      float* disp_old, float* disp_new, uint8_t* dq, uint8_t* label, int* pend, int* counters,
+                      int* tile_stamp, int* last_eval) {
+    __shared__ int s_hist[RV_WARPS][RV_MAXD];
+    __shared__ int s_tot[RV_WARPS];
+    const AdcDims& dm = P.dm;
+    const int pair = blockIdx.x / RV_CLUSTER;
+    const int crank = blockIdx.x % RV_CLUSTER;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int gwarp = crank * RV_WARPS + wid, n_gwarps = RV_CLUSTER * RV_WARPS;
+    const int gtid = crank * RV_THREADS + tid, n_gthreads = RV_CLUSTER * RV_THREADS;
+    const int W = dm.W, D = dm.D;
+    const int tw = (W + RV_TILE - 1) / RV_TILE, th = (dm.H + RV_TILE - 1) / RV_TILE;
+    const int reach = max(P.L1, 0);
+    const uchar4* A = arms + (size_t)pair * dm.N;
+    const uchar2* ALR = alr_all + (size_t)pair * dm.N;
+    float* d_old = disp_old + (size_t)pair * dm.N;
+    float* d_new = disp_new + (size_t)pair * dm.N;
+    uint8_t* q_new = dq + ((size_t)pair * 2 + 0) * dm.N;
+    uint8_t* q_old = dq + ((size_t)pair * 2 + 1) * dm.N;
+    uint8_t* lab = label + (size_t)pair * dm.N;
+    int* tiles = tile_stamp + (size_t)pair * tw * th;
+    int* evalep = last_eval + (size_t)pair * dm.N;
+    int* cnt = counters + pair * ADC_CNT;
+    int n_list[2] = {__ldcg(cnt + 0), __ldcg(cnt + 1)};
+    int rounds_total = 0, evals = 0;
+    int* hist = s_hist[wid];
+
+    for (int i = gtid; i < tw * th; i += n_gthreads) __stcg(tiles + i, 0);
+    for (int k = 0; k < 2; k++) {
+        const int* list = pend + ((size_t)pair * 2 + k) * dm.N;
+        for (int i = gtid; i < n_list[k]; i += n_gthreads) __stcg(evalep + list[i], 0);
+    }
+    if (gtid < 3) __stcg(cnt + 4 + gtid, 0);
+    int epoch = 1, rnd = 0;
+    cluster_sync_all();
+    __threadfence();
+
+    for (int it = 0; it < 5; it++) {
+        for (int k = 0; k < 2; k++) {
+            int* list = pend + ((size_t)pair * 2 + k) * dm.N;
+            const int n = n_list[k];
+            if (n == 0) continue;  // uniform across the cluster
+            bool any_fill = false;
+            while (true) {
+                if (gtid == 0) __stcg(cnt + 4 + (rnd + 1) % 3, 0);
+                bool warp_changed = false;
+                for (int idx = gwarp; idx < n; idx += n_gwarps) {
+                    const int p = __ldca(list + idx);
+                    const int y = p / W, x = p - y * W;
+                    if (__ldca(tiles + (y / RV_TILE) * tw + x / RV_TILE) < __ldca(evalep + p)) continue;
+                    evals++;
+                    for (int b = lane; b < D; b += 32) hist[b] = 0;
+                    __syncwarp();
+                    const uchar4 a = __ldg(A + p);
+                    for (int t = -(int)a.z + lane; t <= (int)a.w; t += 32) {     // one region row per lane
+                        const int rowi = (y + t) * W + x;
+                        const uchar2 a2 = __ldg(ALR + rowi);
+                        const int s_lo = -(int)a2.x, s_hi = (int)a2.y;
+                        const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);   // first s that reads OLD
+#pragma unroll 4
+                        for (int s = s_lo; s <= s_hi; s++) {
+                            const int dv = s < s_mid ? __ldca(q_new + rowi + s) : __ldca(q_old + rowi + s);
+                            if (dv < 254) atomicAdd(&hist[dv], 1);
+                        }
+                    }
+                    __syncwarp();
+                    int peak = 0, best = 0x7fffffff, total = 0;
+                    for (int b = lane; b < D; b += 32) {
+                        const int h = hist[b];
+                        if (peak < h) { peak = h; best = b; }
+                        total += h;
+                    }
+                    const int gpeak = __reduce_max_sync(0xffffffffu, peak);
+                    const int gbest = __reduce_min_sync(0xffffffffu, peak == gpeak ? best : 0x7fffffff);
+                    total = __reduce_add_sync(0xffffffffu, total);
+                    int r = 255;
+                    if (gpeak > 0 && total > P.irv_ts &&
+                        __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th)
+                        r = gbest;
+                    const bool changed = r != (int)__ldcg(q_new + p);
+                    __syncwarp();
+                    if (lane == 0) {
+                        __stcg(evalep + p, epoch);
+                        if (changed) __stcg(q_new + p, (uint8_t)r);
+                    }
+                    if (changed) { rv_stamp_tiles(tiles, tw, th, x, y, reach, epoch, lane); warp_changed = true; }
+                }
+                if (warp_changed && lane == 0) __stcg(cnt + 4 + rnd % 3, 1);
+                cluster_sync_all();
+                __threadfence();   // drop L1 lines that other SMs have overwritten (CCTL.IVALL)
+                const int ch = __ldcg(cnt + 4 + rnd % 3);
+                rounds_total++;
+                epoch++;
+                rnd++;
+                if (!ch) break;
+                any_fill = true;
+            }
+            if (!any_fill) continue;
+            for (int idx = gwarp; idx < n; idx += n_gwarps) {
+                const int p = __ldcg(list + idx);
+                const int v = __ldcg(q_new + p);
+                if (v != 255) {
+                    if (lane == 0) {
+                        const float f = (float)(v + dm.dmin);
+                        __stcg(q_old + p, (uint8_t)v);
+                        __stcg(d_old + p, f);
+                        __stcg(d_new + p, f);
+                        __stcg(lab + p, (uint8_t)0);
+                    }
+                    const int y = p / W;
+                    rv_stamp_tiles(tiles, tw, th, p - y * W, y, reach, epoch, lane);
+                }
+            }
+            epoch++;
+            cluster_sync_all();
+            if (crank == 0) {
+                const int kept = rv_compact_invalid(n, list, d_old, s_tot);
+                if (tid == 0) __stcg(cnt + k, kept);
+            }
+            cluster_sync_all();
+            __threadfence();
+            n_list[k] = __ldcg(cnt + k);
+        }
+    }
+    evals = __reduce_add_sync(0xffffffffu, lane == 0 ? evals : 0);
+    if (lane == 0) atomicAdd(cnt + 3, evals);
+    if (gtid == 0) __stcg(cnt + 2, rounds_total);
 }
 
 __global__ void __cluster_dims__(RV_CLUSTER, 1, 1) __launch_bounds__(RV_THREADS)
@@ -574,9 +716,16 @@ k_region_voting_tiles(AdcParams P, const uchar4* __restrict__ arms, float* disp_
 void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
     // disp_l = committed state (OLD), disp_t = working copy (NEW); both hold the post-outlier map here
     const int reach = P.L1 > 0 ? P.L1 : 0;
-    static int mode = -1;   // development switch: 0 = shared-memory tiles, 1 = global via L1, 2 = global via L2
+    static int mode = -1;   // development switch: 1 = byte state via L1 (default), 0 = shared-memory tiles,
+                            // 2 = float state via L2, 3 = float state via L1
     if (mode < 0) { const char* m = getenv("ADC_VOTE_MODE"); mode = m ? atoi(m) : 1; }
-    if (mode == 0 && P.dm.D <= 254 && reach <= RV_MAXREACH) {
+    dim3 egrid((P.dm.N + 255) / 256, w.S);
+    if (mode == 1 && P.dm.D <= 254) {
+        k_vote_encode<<<egrid, 256, 0, st>>>(P.dm, w.disp_l, w.arms, w.vote_dq, w.vote_alr);
+        k_region_voting_bytes<<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.vote_alr, w.disp_l, w.disp_t, w.vote_dq,
+                                                                      w.label, w.pend, w.counters, w.tile_stamp, w.last_eval);
+        *launches += 2;
+    } else if (mode == 0 && P.dm.D <= 254 && reach <= RV_MAXREACH) {
         const int E = RV_T + 2 * reach;
         const size_t smem = (size_t)E * (E + 1) * 4 + (size_t)RV_WARPS * RV_MAXD * 4 + (size_t)RV_T * RV_T * 2;
         static bool attr_done = false;
@@ -584,13 +733,12 @@ void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, un
             cudaFuncSetAttribute(k_region_voting_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
             attr_done = true;
         }
-        dim3 grid((P.dm.N + 255) / 256, w.S);
-        k_vote_encode<<<grid, 256, 0, st>>>(P.dm, w.disp_l, w.vote_dq);
+        k_vote_encode<<<egrid, 256, 0, st>>>(P.dm, w.disp_l, w.arms, w.vote_dq, w.vote_alr);
         k_region_voting_tiles<<<w.S * RV_CLUSTER, RV_THREADS, smem, st>>>(P, w.arms, w.disp_l, w.disp_t, w.vote_dq, w.label,
                                                                          w.pend, w.counters, w.tile_stamp, w.last_eval);
         *launches += 2;
     } else {
-        if (mode == 2)
+        if (mode != 3)
             k_region_voting_global<false><<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.disp_l, w.disp_t, w.label, w.pend,
                                                                                    w.counters, w.tile_stamp, w.last_eval);
         else
@@ -773,49 +921,58 @@ __device__ __forceinline__ float median9(float v[9]) {
 
 #define MED_PF 8   // wavefront steps between issuing a load and using it
 
+__device__ __forceinline__ void med_cp4(float* smem_dst, const float* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+
 template <int MED_ROWS>   // rows per thread: 1 for H <= 1024, 2 up to 2048
 __global__ void __launch_bounds__(MED_THREADS)
 k_median_wavefront(AdcDims dm, const float* __restrict__ in, float* __restrict__ out) {
-    extern __shared__ float med_ring[];   // [H][4] filtered values of each row, indexed by column & 3
+    extern __shared__ float med_smem[];
+    // [H][4]: filtered values of each row, indexed by column & 3
+    // then per thread and row: MED_PF slots x 2 floats of ORIGINAL values (row y, row y+1) of the column that
+    // enters the window at a given step, filled by 4-byte cp.async issued MED_PF steps ahead
     const int pair = blockIdx.x;
     const float* src = in + (size_t)pair * dm.N;
     float* dst = out + (size_t)pair * dm.N;
     const int W = dm.W, H = dm.H;
+    float* med_ring = med_smem;
+    float* stage = med_smem + (size_t)H * 4 + (size_t)threadIdx.x * (MED_ROWS * MED_PF * 2);
     const float NINF = __int_as_float(0xff800000), PINF = ADC_INVALID_F;
     const int n_steps = W + 2 * H - 2;
-    // per row: a sliding window of ORIGINAL values of row y (columns x, x+1) and row y+1 (x-1, x, x+1),
-    // fed by a ring of loads issued MED_PF steps ahead (slot = step mod MED_PF, the same for every thread)
     float A0[MED_ROWS], A1[MED_ROWS], Bm[MED_ROWS], B0[MED_ROWS], B1[MED_ROWS], left_new[MED_ROWS];
-    float ringA[MED_ROWS][MED_PF], ringB[MED_ROWS][MED_PF];
-    auto fetch = [&](int r, int t, float& a, float& b) {   // originals of column x + 1 = (t - 2y) + 1, consumed at step t
+    auto issue = [&](int r, int t, int slot) {   // originals of column x + 1 = (t - 2y) + 1, consumed at step t
         const int y = threadIdx.x + r * MED_THREADS;
         const int c = t - 2 * y + 1;
+        float* s2 = stage + (r * MED_PF + slot) * 2;
         const bool ok = y < H && c >= 0 && c < W;
-        a = ok ? __ldg(src + y * W + c) : PINF;
-        b = (ok && y + 1 < H) ? __ldg(src + (y + 1) * W + c) : PINF;
+        if (ok) med_cp4(s2, src + y * W + c); else s2[0] = PINF;
+        if (ok && y + 1 < H) med_cp4(s2 + 1, src + (y + 1) * W + c); else s2[1] = PINF;
     };
 #pragma unroll
-    for (int r = 0; r < MED_ROWS; r++) {
-        A0[r] = A1[r] = Bm[r] = B0[r] = B1[r] = PINF;
-        left_new[r] = PINF;
+    for (int r = 0; r < MED_ROWS; r++) { A0[r] = A1[r] = Bm[r] = B0[r] = B1[r] = PINF; left_new[r] = PINF; }
 #pragma unroll
-        for (int j = 0; j < MED_PF; j++) fetch(r, j - 2, ringA[r][j], ringB[r][j]);   // steps -2 .. MED_PF-3
+    for (int j = 0; j < MED_PF; j++) {
+#pragma unroll
+        for (int r = 0; r < MED_ROWS; r++) issue(r, j - 2, j);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
-    // steps start early so that column 0 enters the window (at x = -1) before the first real step
     for (int tb = -2; tb < n_steps; tb += MED_PF) {
 #pragma unroll
         for (int j = 0; j < MED_PF; j++) {
             const int t = tb + j;
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(MED_PF - 1) : "memory");   // this thread's copies for step t
             float res[MED_ROWS];
             bool act[MED_ROWS];
 #pragma unroll
             for (int r = 0; r < MED_ROWS; r++) {
                 const int y = threadIdx.x + r * MED_THREADS;
                 const int x = t - 2 * y;
-                // shift the window: it now holds columns x, x+1 (row y) and x-1, x, x+1 (row y+1)
-                A0[r] = A1[r]; A1[r] = ringA[r][j];
-                Bm[r] = B0[r]; B0[r] = B1[r]; B1[r] = ringB[r][j];
-                fetch(r, t + MED_PF, ringA[r][j], ringB[r][j]);
+                const float* s2 = stage + (r * MED_PF + j) * 2;
+                A0[r] = A1[r]; A1[r] = s2[0];
+                Bm[r] = B0[r]; B0[r] = B1[r]; B1[r] = s2[1];
+                issue(r, t + MED_PF, j);
                 act[r] = t < n_steps && y < H && x >= 0 && x < W;
                 res[r] = 0.f;
                 if (!act[r]) continue;
@@ -832,15 +989,14 @@ k_median_wavefront(AdcDims dm, const float* __restrict__ in, float* __restrict__
                 v[7] = dn ? B0[r] : PINF;
                 v[8] = (dn && rt) ? B1[r] : PINF;
                 const int n = (1 + (int)up + (int)dn) * (1 + (int)lf + (int)rt);
-                // wanted rank n/2 of the n real values == rank 4 of 9 once (4 - n/2) of the absent slots
-                // hold -inf and the others +inf
-                int need = 4 - n / 2;
+                int need = 4 - n / 2;   // rank n/2 of n values == rank 4 of 9 with (4 - n/2) absent slots at -inf
                 const bool present[9] = {up && lf, up, up && rt, lf, true, rt, dn && lf, dn, dn && rt};
 #pragma unroll
                 for (int q = 0; q < 9; q++)
                     if (!present[q] && need > 0) { v[q] = NINF; need--; }
                 res[r] = median9(v);
             }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
             // ring slot (x & 3) of row y holds column x-4, last read by row y+1 one step ago
             __syncthreads();
 #pragma unroll
@@ -855,14 +1011,22 @@ k_median_wavefront(AdcDims dm, const float* __restrict__ in, float* __restrict__
             __syncthreads();
         }
     }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
 int adc_launch_median(const AdcParams& P, const AdcWave& w, const float* in, float* out, cudaStream_t st,
                       unsigned long long* launches) {
     if (P.dm.H > MED_THREADS * 2) return 1;
-    const size_t smem = (size_t)P.dm.H * 4 * sizeof(float);
-    if (P.dm.H <= MED_THREADS) k_median_wavefront<1><<<w.S, MED_THREADS, smem, st>>>(P.dm, in, out);
-    else                       k_median_wavefront<2><<<w.S, MED_THREADS, smem, st>>>(P.dm, in, out);
+    const int rows = P.dm.H <= MED_THREADS ? 1 : 2;
+    const size_t smem = ((size_t)P.dm.H * 4 + (size_t)MED_THREADS * rows * MED_PF * 2) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_median_wavefront<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_median_wavefront<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done = true;
+    }
+    if (rows == 1) k_median_wavefront<1><<<w.S, MED_THREADS, smem, st>>>(P.dm, in, out);
+    else           k_median_wavefront<2><<<w.S, MED_THREADS, smem, st>>>(P.dm, in, out);
     ++*launches;
     return 0;
 }
