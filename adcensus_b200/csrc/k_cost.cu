@@ -86,8 +86,9 @@ k_cost_volume(AdcDims dm, int ppc, const uint8_t* __restrict__ bgr,
     extern __shared__ __align__(16) unsigned char cv_smem[];
     const int pair = blockIdx.y, y = blockIdx.x;
     const int Q = dm.Dp >> 2;                       // threads per pixel
-    const int span = ppc + dm.D - 1;                // right pixels staged per chunk
+    const int span = dm.W + dm.D - 1;               // right-image columns -(dmax-1)-dmin .. : every xr any pixel of the row can ask for
     const int sq = (span + 3) / 4 + 1;              // entries per residue array (padded)
+    const int xr_base = -(dm.D - 1) - dm.dmin;      // image column of staged entry 0 (xr = x - dmin - di, x = 0, di = D-1)
     float* s_ce = reinterpret_cast<float*>(cv_smem);                                      // [64][32]
     float* s_ad = s_ce + 64 * 32;                                                         // [766][CV_AD_REP]
     unsigned long long* s_cen = reinterpret_cast<unsigned long long*>(s_ad + 766 * CV_AD_REP);  // [4][sq]
@@ -100,63 +101,60 @@ k_cost_volume(AdcDims dm, int ppc, const uint8_t* __restrict__ bgr,
     const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) s_ce[i] = __ldg(lut_cen + (i >> 5));
     for (int i = threadIdx.x; i < 766 * CV_AD_REP; i += blockDim.x) s_ad[i] = __ldg(lut_ad + i / CV_AD_REP);
+    // the whole right-image row, once: packed BGR + census, split by (index mod 4)
+    for (int i = threadIdx.x; i < span; i += blockDim.x) {
+        const int xr = xr_base + i;
+        unsigned long long c = 0ull;
+        unsigned pix = 0xffffffffu;                 // marker: outside the image
+        if (xr >= 0 && xr < dm.W) {
+            c = __ldg(cen_r + row + xr);
+            const uchar3 v = adc_load_bgr(right, row + xr);
+            pix = (unsigned)v.x | ((unsigned)v.y << 8) | ((unsigned)v.z << 16);
+        }
+        s_cen[(i & 3) * sq + (i >> 2)] = c;
+        s_bgr[(i & 3) * sq + (i >> 2)] = pix;
+    }
+    __syncthreads();
     const int p = threadIdx.x / Q, q = threadIdx.x - p * Q;
-    for (int x0 = 0; x0 < dm.W; x0 += ppc) {
-        const int xr_base = x0 - (dm.dmax - 1);     // image column of staged entry 0
-        __syncthreads();                            // previous chunk fully consumed (and tables visible)
-        for (int i = threadIdx.x; i < span; i += blockDim.x) {
-            const int xr = xr_base + i;
-            unsigned long long c = 0ull;
-            unsigned pix = 0xffffffffu;             // marker: outside the image
-            if (xr >= 0 && xr < dm.W) {
-                c = __ldg(cen_r + row + xr);
-                const uchar3 v = adc_load_bgr(right, row + xr);
-                pix = (unsigned)v.x | ((unsigned)v.y << 8) | ((unsigned)v.z << 16);
-            }
-            s_cen[(i & 3) * sq + (i >> 2)] = c;
-            s_bgr[(i & 3) * sq + (i >> 2)] = pix;
-        }
-        __syncthreads();
-        const int x = x0 + p;
-        if (p < ppc && x < dm.W) {
-            const uchar3 cl = adc_load_bgr(left, row + x);
-            const unsigned long long bl = __ldg(cen_l + row + x);
-            float out[4];
+    if (p >= ppc) return;
+    for (int x = p; x < dm.W; x += ppc) {
+        const uchar3 cl = adc_load_bgr(left, row + x);
+        const unsigned long long bl = __ldg(cen_l + row + x);
+        float out[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int di = 4 * q + j;
-                float c = 1.0f;                     // out-of-image match: cost_computor.cpp:101-104
-                if (di >= dm.D) c = 0.0f;           // padding lane, never read as a cost
-                else {
-                    const int i = (x - (dm.dmin + di)) - xr_base;
-                    const int si = (i & 3) * sq + (i >> 2);
-                    const unsigned pix = s_bgr[si];
-                    if (pix != 0xffffffffu) {
-                        const int sad = abs((int)cl.x - (int)(pix & 255u)) + abs((int)cl.y - (int)((pix >> 8) & 255u)) +
-                                        abs((int)cl.z - (int)((pix >> 16) & 255u));
-                        const int ham = __popcll(bl ^ s_cen[si]);
-                        c = __fsub_rn(s_ad[sad * CV_AD_REP + (lane & (CV_AD_REP - 1))], s_ce[ham * 32 + lane]);
-                    }
+        for (int j = 0; j < 4; j++) {
+            const int di = 4 * q + j;
+            float c = 1.0f;                         // out-of-image match: cost_computor.cpp:101-104
+            if (di >= dm.D) c = 0.0f;               // padding lane, never read as a cost
+            else {
+                const int i = (x - dm.dmin - di) - xr_base;   // staged index of xr = x - dmin - di, in [0, W+D-2]
+                const int si = (i & 3) * sq + (i >> 2);
+                const unsigned pix = s_bgr[si];
+                if (pix != 0xffffffffu) {
+                    const int sad = abs((int)cl.x - (int)(pix & 255u)) + abs((int)cl.y - (int)((pix >> 8) & 255u)) +
+                                    abs((int)cl.z - (int)((pix >> 16) & 255u));
+                    const int ham = __popcll(bl ^ s_cen[si]);
+                    c = __fsub_rn(s_ad[sad * CV_AD_REP + (lane & (CV_AD_REP - 1))], s_ce[ham * 32 + lane]);
                 }
-                out[j] = c;
             }
-            float4* dst = reinterpret_cast<float4*>(vol + (size_t)pair * dm.vol_stride + ((size_t)row + x) * dm.Dp) + q;
-            *dst = make_float4(out[0], out[1], out[2], out[3]);
+            out[j] = c;
         }
+        float4* dst = reinterpret_cast<float4*>(vol + (size_t)pair * dm.vol_stride + ((size_t)row + x) * dm.Dp) + q;
+        *dst = make_float4(out[0], out[1], out[2], out[3]);
     }
 }
 
 void adc_launch_cost(const AdcParams& P, const AdcWave& w, float* vol, cudaStream_t st, unsigned long long* launches) {
     const int Q = P.dm.Dp / 4;
-    int ppc = 1024 / Q;
+    int ppc = 512 / Q;                              // pixels in flight per CTA
     if (ppc > 32) ppc = 32;
     if (ppc < 1) ppc = 1;
     const int threads = ppc * Q;
-    const int span = ppc + P.dm.D - 1, sq = (span + 3) / 4 + 1;
+    const int span = P.dm.W + P.dm.D - 1, sq = (span + 3) / 4 + 1;
     const size_t smem = (size_t)(64 * 32 + 766 * CV_AD_REP) * 4 + (size_t)4 * sq * 12;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_cost_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(k_cost_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_done = true;
     }
     dim3 grid(P.dm.H, w.S);

@@ -8,6 +8,7 @@
 // result (argument given at each kernel); none of them approximates.
 #include "adc_common.cuh"
 #include <stdlib.h>
+#include <algorithm>
 
 // barrier over all threads of the thread-block cluster, with release/acquire ordering of memory
 __device__ __forceinline__ void cluster_sync_all() {
@@ -381,11 +382,12 @@ __global__ void k_vote_encode(AdcDims dm, const float* __restrict__ disp, const 
 
 // ---------------------------------------------------------------------------------------------
 // Byte-state version of the balanced cluster kernel (default).  Same algorithm as
-// k_region_voting_global, but the working set of a round -- the +-reach rows around the pixels being
-// evaluated -- is 4 bytes per pixel (NEW byte, OLD byte, left/right arm bytes) instead of 12, so it
-// fits the L1 of every SM of the cluster and the dependent loads of an evaluation hit L1 instead of
-// making an L2 round trip each.  Loads are ld.global.ca; the cluster barrier's acquire plus a
-// __threadfence() (CCTL.IVALL) between rounds drop stale lines.
+// k_region_voting_global with two changes that matter for speed: (1) the per-round "does this pending
+// pixel need another look?" test is done 32 list entries at a time, one per lane, instead of one
+// dependent L2 round trip after the other per warp (that serial test loop, not the votes, dominated
+// the first versions); (2) the state is one byte per pixel and the horizontal arms two, so a vote
+// moves 4x fewer bytes.  Mutable state is read at L2 (ld.cg) -- the CTAs of the cluster sit on
+// different SMs -- the constant arms through the read-only path.
 // ---------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(RV_CLUSTER, 1, 1) __launch_bounds__(RV_THREADS)
 k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restrict__ alr_all,
@@ -424,7 +426,6 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
     if (gtid < 3) __stcg(cnt + 4 + gtid, 0);
     int epoch = 1, rnd = 0;
     cluster_sync_all();
-    __threadfence();
 
     for (int it = 0; it < 5; it++) {
         for (int k = 0; k < 2; k++) {
@@ -435,50 +436,63 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
             while (true) {
                 if (gtid == 0) __stcg(cnt + 4 + (rnd + 1) % 3, 0);
                 bool warp_changed = false;
-                for (int idx = gwarp; idx < n; idx += n_gwarps) {
-                    const int p = __ldca(list + idx);
-                    const int y = p / W, x = p - y * W;
-                    if (__ldca(tiles + (y / RV_TILE) * tw + x / RV_TILE) < __ldca(evalep + p)) continue;
-                    evals++;
-                    for (int b = lane; b < D; b += 32) hist[b] = 0;
-                    __syncwarp();
-                    const uchar4 a = __ldg(A + p);
-                    for (int t = -(int)a.z + lane; t <= (int)a.w; t += 32) {     // one region row per lane
-                        const int rowi = (y + t) * W + x;
-                        const uchar2 a2 = __ldg(ALR + rowi);
-                        const int s_lo = -(int)a2.x, s_hi = (int)a2.y;
-                        const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);   // first s that reads OLD
+                // 32 list entries per warp trip: every lane checks one pending pixel (is its tile stamped since
+                // its last evaluation?), then the warp evaluates the dirty ones one after the other
+                for (int base = gwarp * 32; base < n; base += n_gwarps * 32) {
+                    const int my = base + lane;
+                    int p_l = 0;
+                    bool dirty_l = false;
+                    if (my < n) {
+                        p_l = __ldcg(list + my);
+                        const int yy = p_l / W, xx = p_l - yy * W;
+                        dirty_l = __ldcg(tiles + (yy / RV_TILE) * tw + xx / RV_TILE) >= __ldcg(evalep + p_l);
+                    }
+                    unsigned todo = __ballot_sync(0xffffffffu, dirty_l);
+                    while (todo) {
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const int p = __shfl_sync(0xffffffffu, p_l, src);
+                        const int y = p / W, x = p - y * W;
+                        evals++;
+                        for (int b = lane; b < D; b += 32) hist[b] = 0;
+                        __syncwarp();
+                        const uchar4 a = __ldg(A + p);
+                        for (int t = -(int)a.z + lane; t <= (int)a.w; t += 32) {     // one region row per lane
+                            const int rowi = (y + t) * W + x;
+                            const uchar2 a2 = __ldg(ALR + rowi);
+                            const int s_lo = -(int)a2.x, s_hi = (int)a2.y;
+                            const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);   // first s that reads OLD
 #pragma unroll 4
-                        for (int s = s_lo; s <= s_hi; s++) {
-                            const int dv = s < s_mid ? __ldca(q_new + rowi + s) : __ldca(q_old + rowi + s);
-                            if (dv < 254) atomicAdd(&hist[dv], 1);
+                            for (int s = s_lo; s <= s_hi; s++) {
+                                const int dv = s < s_mid ? __ldcg(q_new + rowi + s) : __ldcg(q_old + rowi + s);
+                                if (dv < 254) atomicAdd(&hist[dv], 1);
+                            }
                         }
+                        __syncwarp();
+                        int peak = 0, best = 0x7fffffff, total = 0;
+                        for (int b = lane; b < D; b += 32) {
+                            const int h = hist[b];
+                            if (peak < h) { peak = h; best = b; }
+                            total += h;
+                        }
+                        const int gpeak = __reduce_max_sync(0xffffffffu, peak);
+                        const int gbest = __reduce_min_sync(0xffffffffu, peak == gpeak ? best : 0x7fffffff);
+                        total = __reduce_add_sync(0xffffffffu, total);
+                        int r = 255;
+                        if (gpeak > 0 && total > P.irv_ts &&
+                            __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th)
+                            r = gbest;
+                        const bool changed = r != (int)__ldcg(q_new + p);
+                        __syncwarp();
+                        if (lane == 0) {
+                            __stcg(evalep + p, epoch);
+                            if (changed) __stcg(q_new + p, (uint8_t)r);
+                        }
+                        if (changed) { rv_stamp_tiles(tiles, tw, th, x, y, reach, epoch, lane); warp_changed = true; }
                     }
-                    __syncwarp();
-                    int peak = 0, best = 0x7fffffff, total = 0;
-                    for (int b = lane; b < D; b += 32) {
-                        const int h = hist[b];
-                        if (peak < h) { peak = h; best = b; }
-                        total += h;
-                    }
-                    const int gpeak = __reduce_max_sync(0xffffffffu, peak);
-                    const int gbest = __reduce_min_sync(0xffffffffu, peak == gpeak ? best : 0x7fffffff);
-                    total = __reduce_add_sync(0xffffffffu, total);
-                    int r = 255;
-                    if (gpeak > 0 && total > P.irv_ts &&
-                        __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th)
-                        r = gbest;
-                    const bool changed = r != (int)__ldcg(q_new + p);
-                    __syncwarp();
-                    if (lane == 0) {
-                        __stcg(evalep + p, epoch);
-                        if (changed) __stcg(q_new + p, (uint8_t)r);
-                    }
-                    if (changed) { rv_stamp_tiles(tiles, tw, th, x, y, reach, epoch, lane); warp_changed = true; }
                 }
                 if (warp_changed && lane == 0) __stcg(cnt + 4 + rnd % 3, 1);
                 cluster_sync_all();
-                __threadfence();   // drop L1 lines that other SMs have overwritten (CCTL.IVALL)
                 const int ch = __ldcg(cnt + 4 + rnd % 3);
                 rounds_total++;
                 epoch++;
@@ -509,7 +523,6 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                 if (tid == 0) __stcg(cnt + k, kept);
             }
             cluster_sync_all();
-            __threadfence();
             n_list[k] = __ldcg(cnt + k);
         }
     }
@@ -930,6 +943,7 @@ template <int MED_ROWS>   // rows per thread: 1 for H <= 1024, 2 up to 2048
 __global__ void __launch_bounds__(MED_THREADS)
 k_median_wavefront(AdcDims dm, const float* __restrict__ in, float* __restrict__ out) {
     extern __shared__ float med_smem[];
+    const int MT = blockDim.x;   // threads actually launched (rows rounded up to whole warps)
     // [H][4]: filtered values of each row, indexed by column & 3
     // then per thread and row: MED_PF slots x 2 floats of ORIGINAL values (row y, row y+1) of the column that
     // enters the window at a given step, filled by 4-byte cp.async issued MED_PF steps ahead
@@ -939,11 +953,12 @@ k_median_wavefront(AdcDims dm, const float* __restrict__ in, float* __restrict__
     const int W = dm.W, H = dm.H;
     float* med_ring = med_smem;
     float* stage = med_smem + (size_t)H * 4 + (size_t)threadIdx.x * (MED_ROWS * MED_PF * 2);
+    (void)MT;
     const float NINF = __int_as_float(0xff800000), PINF = ADC_INVALID_F;
     const int n_steps = W + 2 * H - 2;
     float A0[MED_ROWS], A1[MED_ROWS], Bm[MED_ROWS], B0[MED_ROWS], B1[MED_ROWS], left_new[MED_ROWS];
     auto issue = [&](int r, int t, int slot) {   // originals of column x + 1 = (t - 2y) + 1, consumed at step t
-        const int y = threadIdx.x + r * MED_THREADS;
+        const int y = threadIdx.x + r * MT;
         const int c = t - 2 * y + 1;
         float* s2 = stage + (r * MED_PF + slot) * 2;
         const bool ok = y < H && c >= 0 && c < W;
@@ -967,14 +982,16 @@ k_median_wavefront(AdcDims dm, const float* __restrict__ in, float* __restrict__
             bool act[MED_ROWS];
 #pragma unroll
             for (int r = 0; r < MED_ROWS; r++) {
-                const int y = threadIdx.x + r * MED_THREADS;
+                const int y = threadIdx.x + r * MT;
                 const int x = t - 2 * y;
+                act[r] = false;
+                res[r] = 0.f;
+                if (x < -2 - MED_PF || x >= W) continue;   // this row's turn is far away or over: nothing to shift, fetch or compute
                 const float* s2 = stage + (r * MED_PF + j) * 2;
                 A0[r] = A1[r]; A1[r] = s2[0];
                 Bm[r] = B0[r]; B0[r] = B1[r]; B1[r] = s2[1];
                 issue(r, t + MED_PF, j);
                 act[r] = t < n_steps && y < H && x >= 0 && x < W;
-                res[r] = 0.f;
                 if (!act[r]) continue;
                 const bool up = y > 0, dn = y + 1 < H, lf = x > 0, rt = x + 1 < W;
                 float v[9];
@@ -1002,7 +1019,7 @@ k_median_wavefront(AdcDims dm, const float* __restrict__ in, float* __restrict__
 #pragma unroll
             for (int r = 0; r < MED_ROWS; r++) {
                 if (!act[r]) continue;
-                const int y = threadIdx.x + r * MED_THREADS;
+                const int y = threadIdx.x + r * MT;
                 const int x = t - 2 * y;
                 med_ring[(size_t)y * 4 + (x & 3)] = res[r];
                 left_new[r] = res[r];
@@ -1018,15 +1035,16 @@ int adc_launch_median(const AdcParams& P, const AdcWave& w, const float* in, flo
                       unsigned long long* launches) {
     if (P.dm.H > MED_THREADS * 2) return 1;
     const int rows = P.dm.H <= MED_THREADS ? 1 : 2;
-    const size_t smem = ((size_t)P.dm.H * 4 + (size_t)MED_THREADS * rows * MED_PF * 2) * sizeof(float);
+    const int threads = std::min(MED_THREADS, ((P.dm.H + rows - 1) / rows + 31) / 32 * 32);
+    const size_t smem = ((size_t)P.dm.H * 4 + (size_t)threads * rows * MED_PF * 2) * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(k_median_wavefront<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_median_wavefront<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done = true;
     }
-    if (rows == 1) k_median_wavefront<1><<<w.S, MED_THREADS, smem, st>>>(P.dm, in, out);
-    else           k_median_wavefront<2><<<w.S, MED_THREADS, smem, st>>>(P.dm, in, out);
+    if (rows == 1) k_median_wavefront<1><<<w.S, threads, smem, st>>>(P.dm, in, out);
+    else           k_median_wavefront<2><<<w.S, threads, smem, st>>>(P.dm, in, out);
     ++*launches;
     return 0;
 }

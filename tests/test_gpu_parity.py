@@ -50,14 +50,17 @@ CASES = [
     (80, 60, 32, {"do_discontinuity_adjustment": 1}, 10),
     (120, 90, 48, {"lambda_ad": 7, "lambda_census": 20, "so_p1": 0.7, "so_p2": 2.5, "irv_ts": 10,
                    "irv_th": 0.3, "lrcheck_thres": 0.5}, 11),
-    (150, 100, 130, {}, 12),        # K = 5 values per lane in the scanline kernel
+    (150, 100, 130, {}, 12),        # 16 lanes per line, 9 values -> padded stride
+    (80, 60, 32, {"min_disparity": 2, "max_disparity": 34}, 31),     # dmin > 0
+    (80, 60, 32, {"min_disparity": -4, "max_disparity": 28}, 32),    # negative dmin
+    (200, 40, 200, {}, 13),         # a whole warp per line
 ]
 
 
 @pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}x{c[1]}x{c[2]}-{i}" for i, c in enumerate(CASES)])
 def test_stage_parity_synthetic(case):
     w, h, D, over, seed = case
-    opt = T.default_option(max_disparity=D, **over)
+    opt = T.default_option(**{"max_disparity": D, **over})
     left, right = T.synthetic_pair(w, h, D, seed)
     orc = T.Oracle(w, h, opt)
     eng = _engine(w, h, opt)

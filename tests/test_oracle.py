@@ -53,10 +53,12 @@ def test_oracle_cone_final_matches_golden(cone):
 
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("case", [(70, 50, 20, {}, 21), (64, 40, 16, {"min_disparity": 0, "do_lr_check": 0}, 22),
-                                  (90, 64, 40, {"do_filling": 0}, 23), (33, 30, 48, {}, 24), (9, 9, 8, {}, 25)])
+                                  (90, 64, 40, {"do_filling": 0}, 23), (33, 30, 48, {}, 24), (9, 9, 8, {}, 25),
+                                  (80, 60, 32, {"min_disparity": 2, "max_disparity": 34}, 31),
+                                  (80, 60, 32, {"min_disparity": -4, "max_disparity": 28}, 32)])
 def test_oracle_vs_live_reference(case):
     w, h, D, over, seed = case
-    opt = T.default_option(max_disparity=D, **over)
+    opt = T.default_option(**{"max_disparity": D, **over})
     left, right = T.synthetic_pair(w, h, D, seed)
     orc, ref = T.Oracle(w, h, opt), T.Reference(w, h, opt)
     orc.begin(left, right)
