@@ -438,13 +438,18 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                 bool warp_changed = false;
                 // 32 list entries per warp trip: every lane checks one pending pixel (is its tile stamped since
                 // its last evaluation?), then the warp evaluates the dirty ones one after the other
-                for (int base = gwarp * 32; base < n; base += n_gwarps * 32) {
-                    const int my = base + lane;
+                // (entries are dealt so that neighbouring list entries -- neighbouring pixels, which tend to be
+                //  dirty together -- go to different warps: entry = trip*32*n_gwarps + lane*n_gwarps + gwarp)
+                for (int base = 0; base < n; base += n_gwarps * 32) {
+                    const int my = base + lane * n_gwarps + gwarp;
                     int p_l = 0;
+                    unsigned tb_l = 0;
                     bool dirty_l = false;
                     if (my < n) {
                         p_l = __ldcg(list + my);
                         const int yy = p_l / W, xx = p_l - yy * W;
+                        const uchar4 a_l = __ldg(A + p_l);
+                        tb_l = (unsigned)a_l.z | ((unsigned)a_l.w << 8);
                         dirty_l = __ldcg(tiles + (yy / RV_TILE) * tw + xx / RV_TILE) >= __ldcg(evalep + p_l);
                     }
                     unsigned todo = __ballot_sync(0xffffffffu, dirty_l);
@@ -452,17 +457,17 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                         const int src = __ffs(todo) - 1;
                         todo &= todo - 1;
                         const int p = __shfl_sync(0xffffffffu, p_l, src);
+                        const unsigned tb = __shfl_sync(0xffffffffu, tb_l, src);
                         const int y = p / W, x = p - y * W;
                         evals++;
                         for (int b = lane; b < D; b += 32) hist[b] = 0;
                         __syncwarp();
-                        const uchar4 a = __ldg(A + p);
-                        for (int t = -(int)a.z + lane; t <= (int)a.w; t += 32) {     // one region row per lane
+                        for (int t = -(int)(tb & 255u) + lane; t <= (int)(tb >> 8); t += 32) {     // one region row per lane
                             const int rowi = (y + t) * W + x;
                             const uchar2 a2 = __ldg(ALR + rowi);
                             const int s_lo = -(int)a2.x, s_hi = (int)a2.y;
                             const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);   // first s that reads OLD
-#pragma unroll 4
+#pragma unroll 8
                             for (int s = s_lo; s <= s_hi; s++) {
                                 const int dv = s < s_mid ? __ldcg(q_new + rowi + s) : __ldcg(q_old + rowi + s);
                                 if (dv < 254) atomicAdd(&hist[dv], 1);

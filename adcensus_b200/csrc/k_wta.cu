@@ -141,6 +141,7 @@ k_wta_tile(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l
             const float* v = wt_tile + (x - col_lo) * DS;
             float best_cost = ADC_LARGE_F;
             int best = 0;
+#pragma unroll 8
             for (int di = 0; di < dm.D; di++) {
                 const float c = v[di];
                 if (best_cost > c) { best_cost = c; best = dm.dmin + di; }
@@ -156,6 +157,7 @@ k_wta_tile(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l
         if (x < dm.W) {
             float best_cost = ADC_LARGE_F;
             int best = 0;
+#pragma unroll 8
             for (int di = 0; di < dm.D; di++) {
                 const int xl = x + dm.dmin + di;
                 if (xl >= 0 && xl < dm.W) {
