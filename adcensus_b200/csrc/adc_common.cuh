@@ -60,6 +60,7 @@ __device__ __forceinline__ float adc_key2f(unsigned k) {
 struct AdcWave {            // device pointers of one wave (S pairs)
     int S;                  // active pairs in this launch
     uint8_t* bgr;           // [S][2][N*3]
+    unsigned* bgrx;         // [S][2][N] the same pixels packed B | G<<8 | R<<16 (one 32-bit load per pixel)
     uint8_t* gray;          // [S][2][N]
     unsigned long long* census; // [S][2][N]
     float* volA; float* volB;
@@ -81,6 +82,7 @@ struct AdcWave {            // device pointers of one wave (S pairs)
     const float* lut_ad;    // [766]  (1 - exp(-(s/3)/lambda_ad)) + 1, host libm expf
     const float* lut_cen;   // [64]   exp(-h/lambda_census)
     const double* ray_sin; const double* ray_cos; // [16] host libm sin/cos of the accumulated angles
+    const short2* ray_off;  // [16][max_search] (dx,dy) = (lround(m*cos), lround(m*sin)); NULL if not verified exact
 };
 
 void adc_launch_gray_census(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);

@@ -78,6 +78,7 @@ struct adc_engine {
     float* d_lut_ad = nullptr;
     float* d_lut_cen = nullptr;
     double* d_rays = nullptr;  // [32]: sin[16], cos[16]
+    short2* d_ray_off = nullptr;  // [16][max_search] integer ray offsets, when verified exact for this image size
     unsigned long long launches = 0;
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t ev_stage[8] = {};
@@ -111,6 +112,7 @@ size_t carve_lane(void* base, const AdcDims& dm, int S, AdcWave* w) {
     t.volB = c.take<float>((size_t)S * dm.vol_stride);
     t.bgr = c.take<uint8_t>((size_t)S * 2 * N * 3);
     t.gray = c.take<uint8_t>((size_t)S * 2 * N);
+    t.bgrx = c.take<unsigned>((size_t)S * 2 * N);
     t.census = c.take<unsigned long long>((size_t)S * 2 * N);
     t.arms = c.take<uchar4>((size_t)S * N);
     t.sup_h = c.take<uint16_t>((size_t)S * N);
@@ -183,6 +185,25 @@ int upload_tables(adc_engine* e) {
     CK(cudaMemcpy(e->d_lut_ad, ad.data(), sizeof(float) * 766, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(e->d_lut_cen, cen.data(), sizeof(float) * 64, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(e->d_rays, rays, sizeof(double) * 32, cudaMemcpyHostToDevice));
+    // ProperInterpolation evaluates lround(y + m*sin) per step (multistep_refiner.cpp:252-254).  For integer y
+    // that equals y + lround(m*sin) unless a rounding of the double sum (or a half-way case) intervenes;
+    // check every (ray, m, coordinate) the image can produce and only then let the kernel use the table.
+    const int L = e->P.max_search;
+    if (L > 1 && L < 4096) {
+        std::vector<short2> off((size_t)16 * L);
+        bool exact = true;
+        for (int s = 0; s < 16 && exact; s++)
+            for (int m = 1; m < L && exact; m++) {
+                const long dy = lround(m * rays[s]), dx = lround(m * rays[16 + s]);
+                for (int y = 0; y < e->H && exact; y++) exact = lround(y + m * rays[s]) == y + dy;
+                for (int x = 0; x < e->W && exact; x++) exact = lround(x + m * rays[16 + s]) == x + dx;
+                off[(size_t)s * L + m] = make_short2((short)dx, (short)dy);
+            }
+        if (exact) {
+            CK(cudaMalloc(&e->d_ray_off, sizeof(short2) * off.size()));
+            CK(cudaMemcpy(e->d_ray_off, off.data(), sizeof(short2) * off.size(), cudaMemcpyHostToDevice));
+        }
+    }
     return ADC_OK;
 }
 
@@ -193,6 +214,7 @@ AdcWave wave_view(const adc_engine* e, const Lane& ln, int nS) {
     w.lut_cen = e->d_lut_cen;
     w.ray_sin = e->d_rays;
     w.ray_cos = e->d_rays + 16;
+    w.ray_off = e->d_ray_off;
     return w;
 }
 
@@ -405,6 +427,7 @@ void adc_destroy(adc_engine* e) {
     if (e->d_lut_ad) cudaFree(e->d_lut_ad);
     if (e->d_lut_cen) cudaFree(e->d_lut_cen);
     if (e->d_rays) cudaFree(e->d_rays);
+    if (e->d_ray_off) cudaFree(e->d_ray_off);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     for (auto& ev : e->ev_stage) if (ev) cudaEventDestroy(ev);
     if (e->main_st) cudaStreamDestroy(e->main_st);

@@ -22,7 +22,7 @@ __device__ __forceinline__ uint8_t gray_of(const uint8_t* __restrict__ px) {
 
 __global__ void __launch_bounds__(CT_W* CT_H)
 k_gray_census(AdcDims dm, const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray,
-              unsigned long long* __restrict__ census) {
+              unsigned long long* __restrict__ census, unsigned* __restrict__ bgrx) {
     __shared__ uint8_t tile[CT_H + 2 * CT_HY][CT_W + 2 * CT_HX + 2];
     const int img = blockIdx.z;  // pair*2 + view
     const uint8_t* src = bgr + (size_t)img * dm.N * 3;
@@ -44,6 +44,10 @@ k_gray_census(AdcDims dm, const uint8_t* __restrict__ bgr, uint8_t* __restrict__
     const int tx = threadIdx.x + CT_HX, ty = threadIdx.y + CT_HY;
     const uint8_t centre = tile[ty][tx];
     g_out[(size_t)y * dm.W + x] = centre;
+    {   // packed copy of the pixel (B | G<<8 | R<<16) for the kernels that compare colours
+        const uint8_t* px = src + ((size_t)y * dm.W + x) * 3;
+        bgrx[(size_t)img * dm.N + (size_t)y * dm.W + x] = (unsigned)__ldg(px) | ((unsigned)__ldg(px + 1) << 8) | ((unsigned)__ldg(px + 2) << 16);
+    }
     unsigned long long bits = 0ull;
     // border pixels keep 0 and tiny images are skipped entirely (adcensus_util.cpp:12,17-18)
     if (dm.W > 9 && dm.H > 7 && y >= 4 && y < dm.H - 4 && x >= 3 && x < dm.W - 3) {
@@ -58,7 +62,7 @@ k_gray_census(AdcDims dm, const uint8_t* __restrict__ bgr, uint8_t* __restrict__
 
 void adc_launch_gray_census(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
     dim3 grid((P.dm.W + CT_W - 1) / CT_W, (P.dm.H + CT_H - 1) / CT_H, w.S * 2), block(CT_W, CT_H);
-    k_gray_census<<<grid, block, 0, st>>>(P.dm, w.bgr, w.gray, w.census);
+    k_gray_census<<<grid, block, 0, st>>>(P.dm, w.bgr, w.gray, w.census, w.bgrx);
     ++*launches;
 }
 
@@ -80,7 +84,7 @@ void adc_launch_gray_census(const AdcParams& P, const AdcWave& w, cudaStream_t s
 #define CV_AD_REP 8
 
 __global__ void __launch_bounds__(1024)
-k_cost_volume(AdcDims dm, int ppc, const uint8_t* __restrict__ bgr,
+k_cost_volume(AdcDims dm, int ppc, const unsigned* __restrict__ bgrx,
               const unsigned long long* __restrict__ census, float* __restrict__ vol,
               const float* __restrict__ lut_ad, const float* __restrict__ lut_cen) {
     extern __shared__ __align__(16) unsigned char cv_smem[];
@@ -93,8 +97,8 @@ k_cost_volume(AdcDims dm, int ppc, const uint8_t* __restrict__ bgr,
     float* s_ad = s_ce + 64 * 32;                                                         // [766][CV_AD_REP]
     unsigned long long* s_cen = reinterpret_cast<unsigned long long*>(s_ad + 766 * CV_AD_REP);  // [4][sq]
     unsigned* s_bgr = reinterpret_cast<unsigned*>(s_cen + 4 * sq);                        // [4][sq]
-    const uint8_t* left = bgr + (size_t)pair * 2 * dm.N * 3;
-    const uint8_t* right = left + (size_t)dm.N * 3;
+    const unsigned* left = bgrx + (size_t)pair * 2 * dm.N;
+    const unsigned* right = left + (size_t)dm.N;
     const unsigned long long* cen_l = census + (size_t)pair * 2 * dm.N;
     const unsigned long long* cen_r = cen_l + dm.N;
     const int row = y * dm.W;
@@ -108,8 +112,7 @@ k_cost_volume(AdcDims dm, int ppc, const uint8_t* __restrict__ bgr,
         unsigned pix = 0xffffffffu;                 // marker: outside the image
         if (xr >= 0 && xr < dm.W) {
             c = __ldg(cen_r + row + xr);
-            const uchar3 v = adc_load_bgr(right, row + xr);
-            pix = (unsigned)v.x | ((unsigned)v.y << 8) | ((unsigned)v.z << 16);
+            pix = __ldg(right + row + xr);
         }
         s_cen[(i & 3) * sq + (i >> 2)] = c;
         s_bgr[(i & 3) * sq + (i >> 2)] = pix;
@@ -118,7 +121,7 @@ k_cost_volume(AdcDims dm, int ppc, const uint8_t* __restrict__ bgr,
     const int p = threadIdx.x / Q, q = threadIdx.x - p * Q;
     if (p >= ppc) return;
     for (int x = p; x < dm.W; x += ppc) {
-        const uchar3 cl = adc_load_bgr(left, row + x);
+        const unsigned cl = __ldg(left + row + x);
         const unsigned long long bl = __ldg(cen_l + row + x);
         float out[4];
 #pragma unroll
@@ -131,8 +134,7 @@ k_cost_volume(AdcDims dm, int ppc, const uint8_t* __restrict__ bgr,
                 const int si = (i & 3) * sq + (i >> 2);
                 const unsigned pix = s_bgr[si];
                 if (pix != 0xffffffffu) {
-                    const int sad = abs((int)cl.x - (int)(pix & 255u)) + abs((int)cl.y - (int)((pix >> 8) & 255u)) +
-                                    abs((int)cl.z - (int)((pix >> 16) & 255u));
+                    const int sad = (int)__vsadu4(cl, pix);     // |dB| + |dG| + |dR| (4th byte is 0 in both)
                     const int ham = __popcll(bl ^ s_cen[si]);
                     c = __fsub_rn(s_ad[sad * CV_AD_REP + (lane & (CV_AD_REP - 1))], s_ce[ham * 32 + lane]);
                 }
@@ -158,7 +160,7 @@ void adc_launch_cost(const AdcParams& P, const AdcWave& w, float* vol, cudaStrea
         attr_done = true;
     }
     dim3 grid(P.dm.H, w.S);
-    k_cost_volume<<<grid, threads, smem, st>>>(P.dm, ppc, w.bgr, w.census, vol, w.lut_ad, w.lut_cen);
+    k_cost_volume<<<grid, threads, smem, st>>>(P.dm, ppc, w.bgrx, w.census, vol, w.lut_ad, w.lut_cen);
     ++*launches;
 }
 

@@ -462,15 +462,42 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                         evals++;
                         for (int b = lane; b < D; b += 32) hist[b] = 0;
                         __syncwarp();
-                        for (int t = -(int)(tb & 255u) + lane; t <= (int)(tb >> 8); t += 32) {     // one region row per lane
-                            const int rowi = (y + t) * W + x;
-                            const uchar2 a2 = __ldg(ALR + rowi);
-                            const int s_lo = -(int)a2.x, s_hi = (int)a2.y;
-                            const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);   // first s that reads OLD
-#pragma unroll 8
-                            for (int s = s_lo; s <= s_hi; s++) {
-                                const int dv = s < s_mid ? __ldcg(q_new + rowi + s) : __ldcg(q_old + rowi + s);
-                                if (dv < 254) atomicAdd(&hist[dv], 1);
+                        // Region scan: the horizontal arms of all (<= 69) region rows are fetched in ONE round of
+                        // loads, three per lane at most, and handed out by shuffle; then 4 rows x 8 columns of the
+                        // region are visited per trip (the first two 8-column chunks of a row are loaded together).
+                        const int top = (int)(tb & 255u), rows = top + (int)(tb >> 8) + 1;
+                        const int rbase = (y - top) * W + x;
+                        unsigned ar[3];
+#pragma unroll
+                        for (int j = 0; j < 3; j++) {
+                            const int ri = lane + 32 * j;
+                            const uchar2 v = ri < rows ? __ldg(ALR + rbase + ri * W) : make_uchar2(0, 0);
+                            ar[j] = (unsigned)v.x | ((unsigned)v.y << 8);
+                        }
+                        const int grp = lane >> 3, sub = lane & 7;
+                        for (int ri0 = 0; ri0 < rows; ri0 += 4) {
+                            const int ri = ri0 + grp;
+                            unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
+                            if (rows > 32) {
+                                const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31);
+                                const unsigned a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
+                                a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
+                            }
+                            if (ri < rows) {
+                                const int t = ri - top;
+                                const int rowi = rbase + ri * W;
+                                const int s_lo = -(int)(a2 & 255u), s_hi = (int)(a2 >> 8);
+                                const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);   // first s that reads OLD
+                                const int s0 = s_lo + sub, s1 = s0 + 8;
+                                int d0 = 255, d1 = 255;
+                                if (s0 <= s_hi) d0 = s0 < s_mid ? __ldcg(q_new + rowi + s0) : __ldcg(q_old + rowi + s0);
+                                if (s1 <= s_hi) d1 = s1 < s_mid ? __ldcg(q_new + rowi + s1) : __ldcg(q_old + rowi + s1);
+                                if (d0 < 254) atomicAdd(&hist[d0], 1);
+                                if (d1 < 254) atomicAdd(&hist[d1], 1);
+                                for (int sx = s1 + 8; sx <= s_hi; sx += 8) {
+                                    const int dv = sx < s_mid ? __ldcg(q_new + rowi + sx) : __ldcg(q_old + rowi + sx);
+                                    if (dv < 254) atomicAdd(&hist[dv], 1);
+                                }
                             }
                         }
                         __syncwarp();
@@ -780,7 +807,8 @@ void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, un
 __global__ void __launch_bounds__(256)
 k_interpolate(AdcParams P, int k, const uint8_t* __restrict__ bgr, const float* __restrict__ disp_old,
               float* __restrict__ disp_new, const int* __restrict__ pend, const int* __restrict__ counters,
-              const double* __restrict__ ray_sin, const double* __restrict__ ray_cos) {
+              const double* __restrict__ ray_sin, const double* __restrict__ ray_cos,
+              const short2* __restrict__ ray_off) {
     const AdcDims& dm = P.dm;
     const int pair = blockIdx.y;
     const int n = counters[pair * ADC_CNT + k];
@@ -804,8 +832,14 @@ k_interpolate(AdcParams P, int k, const uint8_t* __restrict__ bgr, const float* 
         if (active) {
             const uchar3 c0 = adc_load_bgr(left, p);
             for (int m = 1; m < P.max_search; m++) {
-                const long yy = lround(__dadd_rn((double)y, __dmul_rn((double)m, sa)));
-                const long xx = lround(__dadd_rn((double)x, __dmul_rn((double)m, ca)));
+                long yy, xx;
+                if (ray_off) {   // integer offsets, verified on the host to equal the expression below for this image size
+                    const short2 o = __ldg(ray_off + ray * P.max_search + m);
+                    yy = y + o.y; xx = x + o.x;
+                } else {
+                    yy = lround(__dadd_rn((double)y, __dmul_rn((double)m, sa)));
+                    xx = lround(__dadd_rn((double)x, __dmul_rn((double)m, ca)));
+                }
                 if (yy < 0 || yy >= dm.H || xx < 0 || xx >= dm.W) break;
                 const int q = (int)yy * dm.W + (int)xx;
                 const float d = d_old[q];
@@ -841,8 +875,8 @@ k_interpolate(AdcParams P, int k, const uint8_t* __restrict__ bgr, const float* 
 }
 
 void adc_launch_interp_list(const AdcParams& P, const AdcWave& w, int k, cudaStream_t st, unsigned long long* launches) {
-    dim3 grid(148, w.S);
-    k_interpolate<<<grid, 256, 0, st>>>(P, k, w.bgr, w.disp_l, w.disp_t, w.pend, w.counters, w.ray_sin, w.ray_cos);
+    dim3 grid(592, w.S);
+    k_interpolate<<<grid, 256, 0, st>>>(P, k, w.bgr, w.disp_l, w.disp_t, w.pend, w.counters, w.ray_sin, w.ray_cos, w.ray_off);
     ++*launches;
 }
 

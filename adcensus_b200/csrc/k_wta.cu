@@ -115,13 +115,13 @@ k_wta_right_finish(AdcDims dm, const float* __restrict__ vol, const unsigned lon
 // view down its own column vector, for the right view along the diagonal cost_L(xr + d, d) -- with
 // the reference's strict '>' comparison.  The halo columns are read twice (second time from L2).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(2 * WT_PX)
-k_wta_tile(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, float* __restrict__ disp_r) {
+__global__ void __launch_bounds__(256)
+k_wta_tile(AdcDims dm, int wpx, const float* __restrict__ vol, float* __restrict__ disp_l, float* __restrict__ disp_r) {
     extern __shared__ float wt_tile[];
-    const int pair = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * WT_PX;
+    const int pair = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * wpx;
     const int Q = dm.Dp >> 2, DS = dm.Dp + 1;
     const int col_lo = x0 + min(0, dm.dmin);
-    const int col_hi = x0 + WT_PX - 1 + max(0, dm.dmax - 1);
+    const int col_hi = x0 + wpx - 1 + max(0, dm.dmax - 1);
     const int ncols = col_hi - col_lo + 1;
     const float* rowv = vol + (size_t)pair * dm.vol_stride + (size_t)y * dm.W * dm.Dp;
     for (int i = threadIdx.x; i < ncols * Q; i += blockDim.x) {
@@ -135,7 +135,7 @@ k_wta_tile(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l
     }
     __syncthreads();
     const int t = threadIdx.x;
-    if (t < WT_PX) {                                   // ---- left view (ADCensusStereo.cpp:188-243)
+    if (t < wpx) {                                   // ---- left view (ADCensusStereo.cpp:188-243)
         const int x = x0 + t;
         if (x < dm.W) {
             const float* v = wt_tile + (x - col_lo) * DS;
@@ -153,7 +153,7 @@ k_wta_tile(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l
             disp_l[(size_t)pair * dm.N + y * dm.W + x] = out;
         }
     } else {                                           // ---- right view (ADCensusStereo.cpp:245-310)
-        const int x = x0 + t - WT_PX;
+        const int x = x0 + t - wpx;
         if (x < dm.W) {
             float best_cost = ADC_LARGE_F;
             int best = 0;
@@ -179,16 +179,18 @@ k_wta_tile(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l
 }
 
 int adc_launch_wta(const AdcParams& P, const AdcWave& w, const float* vol, cudaStream_t st, unsigned long long* launches) {
-    const int ncols = WT_PX + (P.dm.dmax - 1 > 0 ? P.dm.dmax - 1 : 0) - (P.dm.dmin < 0 ? P.dm.dmin : 0);
-    const size_t tile_bytes = (size_t)ncols * (P.dm.Dp + 1) * sizeof(float);
+    const int extra = (P.dm.dmax - 1 > 0 ? P.dm.dmax - 1 : 0) - (P.dm.dmin < 0 ? P.dm.dmin : 0);
+    int wpx = 128;                                   // output pixels per CTA: as many as keep the tile small
+    while (wpx > 32 && (size_t)(wpx + extra) * (P.dm.Dp + 1) * sizeof(float) > 64 * 1024) wpx >>= 1;
+    const size_t tile_bytes = (size_t)(wpx + extra) * (P.dm.Dp + 1) * sizeof(float);
     if (tile_bytes <= 200 * 1024) {
         static bool attr_done = false;
         if (!attr_done) {
             cudaFuncSetAttribute(k_wta_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr_done = true;
         }
-        dim3 grid((P.dm.W + WT_PX - 1) / WT_PX, P.dm.H, w.S);
-        k_wta_tile<<<grid, 2 * WT_PX, tile_bytes, st>>>(P.dm, vol, w.disp_l, w.disp_r);
+        dim3 grid((P.dm.W + wpx - 1) / wpx, P.dm.H, w.S);
+        k_wta_tile<<<grid, 2 * wpx, tile_bytes, st>>>(P.dm, wpx, vol, w.disp_l, w.disp_r);
         ++*launches;
         return 0;
     }
