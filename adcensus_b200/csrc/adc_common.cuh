@@ -70,6 +70,7 @@ struct AdcWave {            // device pointers of one wave (S pairs)
     float* disp_l; float* disp_r; float* disp_t;
     uint8_t* label; uint8_t* flag;
     int* pend;              // [S][2][N] mismatch / occlusion pixel lists (raster order)
+    int* vlist;             // [S][2][N] the sub-lists region voting works on (pixels that can still be filled)
     int* counters;          // [S][ADC_CNT]: 0,1 list sizes; 2 voting rounds; 3 voting evaluations; 4.. flags/queues
     int* rowcnt;            // [S][2][H] per-row list counts / offsets
     unsigned* so_bitrows;   // [S][4][H][row words] mirrored per-row bit vectors of the right image (scanline optimiser)

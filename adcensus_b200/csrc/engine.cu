@@ -124,6 +124,7 @@ size_t carve_lane(void* base, const AdcDims& dm, int S, AdcWave* w) {
     t.label = c.take<uint8_t>((size_t)S * N);
     t.flag = c.take<uint8_t>((size_t)S * N);
     t.pend = c.take<int>((size_t)S * 2 * N);
+    t.vlist = c.take<int>((size_t)S * 2 * N);
     t.counters = c.take<int>((size_t)S * ADC_CNT);
     t.vote_dq = c.take<uint8_t>((size_t)S * 2 * N);
     t.vote_alr = c.take<uchar2>((size_t)S * N);

@@ -104,11 +104,18 @@ void adc_launch_outlier(const AdcParams& P, const AdcWave& w, cudaStream_t st, u
 
 // ---- ordered (raster) pixel lists of the two outlier classes: row counts -> scan -> scatter ----
 __global__ void __launch_bounds__(128)
-k_list_row_counts(AdcDims dm, const uint8_t* __restrict__ label, int* __restrict__ rowcnt) {
+k_list_row_counts(AdcDims dm, const uint8_t* __restrict__ label, const uint16_t* __restrict__ region_size, int min_size,
+                  int* __restrict__ rowcnt) {
+    // region_size != NULL: only pixels whose cross region holds more than min_size pixels (see adc_launch_voting)
     const int pair = blockIdx.y, y = blockIdx.x;
     const uint8_t* lab = label + (size_t)pair * dm.N + (size_t)y * dm.W;
+    const uint16_t* rs = region_size ? region_size + (size_t)pair * dm.N + (size_t)y * dm.W : nullptr;
     int c1 = 0, c2 = 0;
-    for (int x = threadIdx.x; x < dm.W; x += 128) { const uint8_t v = lab[x]; c1 += v == 1; c2 += v == 2; }
+    for (int x = threadIdx.x; x < dm.W; x += 128) {
+        uint8_t v = lab[x];
+        if (rs && (int)rs[x] <= min_size) v = 0;
+        c1 += v == 1; c2 += v == 2;
+    }
     __shared__ int s1[4], s2[4];
     c1 = __reduce_add_sync(0xffffffffu, c1);
     c2 = __reduce_add_sync(0xffffffffu, c2);
@@ -122,7 +129,7 @@ k_list_row_counts(AdcDims dm, const uint8_t* __restrict__ label, int* __restrict
 
 // exclusive scan of the row counts (in place), one warp per (pair, class)
 __global__ void __launch_bounds__(64)
-k_list_row_scan(AdcDims dm, int* __restrict__ rowcnt, int* __restrict__ counters) {
+k_list_row_scan(AdcDims dm, int* __restrict__ rowcnt, int* __restrict__ counters, int slot) {
     const int pair = blockIdx.x, k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int* rc = rowcnt + ((size_t)pair * 2 + k) * dm.H;
     int base = 0;
@@ -135,13 +142,15 @@ k_list_row_scan(AdcDims dm, int* __restrict__ rowcnt, int* __restrict__ counters
         if (y < dm.H) rc[y] = base + inc - v;
         base += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) counters[pair * ADC_CNT + k] = base;
+    if (lane == 0) counters[pair * ADC_CNT + slot + k] = base;
 }
 
 __global__ void __launch_bounds__(128)
-k_list_row_scatter(AdcDims dm, const uint8_t* __restrict__ label, const int* __restrict__ rowoff, int* __restrict__ pend) {
+k_list_row_scatter(AdcDims dm, const uint8_t* __restrict__ label, const uint16_t* __restrict__ region_size, int min_size,
+                   const int* __restrict__ rowoff, int* __restrict__ pend) {
     const int pair = blockIdx.y, y = blockIdx.x;
     const uint8_t* lab = label + (size_t)pair * dm.N + (size_t)y * dm.W;
+    const uint16_t* rs = region_size ? region_size + (size_t)pair * dm.N + (size_t)y * dm.W : nullptr;
     __shared__ int s_cnt[2][4];
     int base1 = rowoff[((size_t)pair * 2 + 0) * dm.H + y], base2 = rowoff[((size_t)pair * 2 + 1) * dm.H + y];
     int* l1 = pend + ((size_t)pair * 2 + 0) * dm.N;
@@ -149,7 +158,8 @@ k_list_row_scatter(AdcDims dm, const uint8_t* __restrict__ label, const int* __r
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int x0 = 0; x0 < dm.W; x0 += 128) {
         const int x = x0 + threadIdx.x;
-        const uint8_t v = x < dm.W ? lab[x] : 0;
+        uint8_t v = x < dm.W ? lab[x] : 0;
+        if (rs && x < dm.W && (int)rs[x] <= min_size) v = 0;
         const unsigned b1 = __ballot_sync(0xffffffffu, v == 1), b2 = __ballot_sync(0xffffffffu, v == 2);
         if (lane == 0) { s_cnt[0][wid] = __popc(b1); s_cnt[1][wid] = __popc(b2); }
         __syncthreads();
@@ -169,9 +179,24 @@ k_list_row_scatter(AdcDims dm, const uint8_t* __restrict__ label, const int* __r
 
 void adc_launch_build_lists(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
     dim3 grid(P.dm.H, w.S);
-    k_list_row_counts<<<grid, 128, 0, st>>>(P.dm, w.label, w.rowcnt);
-    k_list_row_scan<<<w.S, 64, 0, st>>>(P.dm, w.rowcnt, w.counters);
-    k_list_row_scatter<<<grid, 128, 0, st>>>(P.dm, w.label, w.rowcnt, w.pend);
+    k_list_row_counts<<<grid, 128, 0, st>>>(P.dm, w.label, nullptr, 0, w.rowcnt);
+    k_list_row_scan<<<w.S, 64, 0, st>>>(P.dm, w.rowcnt, w.counters, 0);
+    k_list_row_scatter<<<grid, 128, 0, st>>>(P.dm, w.label, nullptr, 0, w.rowcnt, w.pend);
+    *launches += 3;
+}
+
+// Lists of the pixels that can still be filled by voting: a vote needs more than irv_ts valid pixels in
+// the pixel's cross region (multistep_refiner.cpp:211), and that region -- the vertical arm of p, then the
+// horizontal arm of every pixel on it -- is exactly the horizontal-first support region whose size
+// cross_aggregator.cpp:271-325 already counted.  A pixel whose whole region is not larger than irv_ts can
+// never pass, in any sweep, whatever its neighbours become: it is left out of the voting lists (about 40 %
+// of the listed pixels on Cone) and simply stays in the outlier lists for the interpolation step.
+static void launch_active_lists(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
+    const bool exact = P.L1 <= 127;   // beyond that the reference's uint16 counts may wrap
+    dim3 grid(P.dm.H, w.S);
+    k_list_row_counts<<<grid, 128, 0, st>>>(P.dm, w.label, exact ? w.sup_h : nullptr, P.irv_ts, w.rowcnt);
+    k_list_row_scan<<<w.S, 64, 0, st>>>(P.dm, w.rowcnt, w.counters, 10);
+    k_list_row_scatter<<<grid, 128, 0, st>>>(P.dm, w.label, exact ? w.sup_h : nullptr, P.irv_ts, w.rowcnt, w.vlist);
     *launches += 3;
 }
 
@@ -414,7 +439,7 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
     int* tiles = tile_stamp + (size_t)pair * tw * th;
     int* evalep = last_eval + (size_t)pair * dm.N;
     int* cnt = counters + pair * ADC_CNT;
-    int n_list[2] = {__ldcg(cnt + 0), __ldcg(cnt + 1)};
+    int n_list[2] = {__ldcg(cnt + 10), __ldcg(cnt + 11)};   // active (fillable) lists, see launch_active_lists
     int rounds_total = 0, evals = 0;
     int* hist = s_hist[wid];
 
@@ -552,10 +577,10 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
             cluster_sync_all();
             if (crank == 0) {
                 const int kept = rv_compact_invalid(n, list, d_old, s_tot);
-                if (tid == 0) __stcg(cnt + k, kept);
+                if (tid == 0) __stcg(cnt + 10 + k, kept);
             }
             cluster_sync_all();
-            n_list[k] = __ldcg(cnt + k);
+            n_list[k] = __ldcg(cnt + 10 + k);
         }
     }
     evals = __reduce_add_sync(0xffffffffu, lane == 0 ? evals : 0);
@@ -592,7 +617,7 @@ k_region_voting_tiles(AdcParams P, const uchar4* __restrict__ arms, float* disp_
     int* stamps = tile_stamp + (size_t)pair * n_tiles;
     int* evals_ep = tile_eval + (size_t)pair * 2 * n_tiles;
     int* cnt = counters + pair * ADC_CNT;  // 0,1 list sizes; 2 rounds; 3 evaluations; 4..6 change flags; 7..9 tile queues
-    int n_list[2] = {__ldcg(cnt + 0), __ldcg(cnt + 1)};
+    int n_list[2] = {__ldcg(cnt + 10), __ldcg(cnt + 11)};   // active (fillable) lists, see launch_active_lists
     int rounds_total = 0, evals = 0;
     int* hist = s_hist_base + wid * RV_MAXD;
     const int grp = lane >> 3, sub = lane & 7;
@@ -747,10 +772,10 @@ k_region_voting_tiles(AdcParams P, const uchar4* __restrict__ arms, float* disp_
             cluster_sync_all();
             if (crank == 0) {
                 const int kept = rv_compact_invalid(n, list, d_old, s_tot);
-                if (tid == 0) __stcg(cnt + k, kept);
+                if (tid == 0) __stcg(cnt + 10 + k, kept);
             }
             cluster_sync_all();
-            n_list[k] = __ldcg(cnt + k);
+            n_list[k] = __ldcg(cnt + 10 + k);
         }
     }
     evals = __reduce_add_sync(0xffffffffu, lane == 0 ? evals : 0);
@@ -766,10 +791,12 @@ void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, un
     if (mode < 0) { const char* m = getenv("ADC_VOTE_MODE"); mode = m ? atoi(m) : 1; }
     dim3 egrid((P.dm.N + 255) / 256, w.S);
     if (mode == 1 && P.dm.D <= 254) {
+        launch_active_lists(P, w, st, launches);
         k_vote_encode<<<egrid, 256, 0, st>>>(P.dm, w.disp_l, w.arms, w.vote_dq, w.vote_alr);
         k_region_voting_bytes<<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.vote_alr, w.disp_l, w.disp_t, w.vote_dq,
-                                                                      w.label, w.pend, w.counters, w.tile_stamp, w.last_eval);
+                                                                      w.label, w.vlist, w.counters, w.tile_stamp, w.last_eval);
         *launches += 2;
+        adc_launch_build_lists(P, w, st, launches);   // outlier lists = every listed pixel that is still invalid
     } else if (mode == 0 && P.dm.D <= 254 && reach <= RV_MAXREACH) {
         const int E = RV_T + 2 * reach;
         const size_t smem = (size_t)E * (E + 1) * 4 + (size_t)RV_WARPS * RV_MAXD * 4 + (size_t)RV_T * RV_T * 2;

@@ -11,6 +11,7 @@ static arm_t* arms; static float *d_old, *d_new; static uint8_t* label;
 static int ts = 20; static float th = 0.4f;
 static int hist[512];
 static long evals = 0;
+static int last_peak, last_total;
 static float vote(int p, const float* newv, const float* oldv) {
     int y = p / W, x = p % W;
     memset(hist, 0, sizeof(int) * D);
@@ -25,7 +26,7 @@ static float vote(int p, const float* newv, const float* oldv) {
     }
     int best = 0, tot = 0, peak = 0;
     for (int d = 0; d < D; d++) { if (peak < hist[d]) { peak = hist[d]; best = d; } tot += hist[d]; }
-    evals++;
+    evals++; last_peak = peak; last_total = tot;
     if (peak > 0 && tot > ts && (float)peak / (float)tot > th) return (float)best;
     return INFINITY;
 }
@@ -37,10 +38,25 @@ int main(int argc, char** argv) {
     memcpy(d_new, d_old, N * 4);
     int* lists[2]; int n[2] = {0, 0};
     for (int k = 0; k < 2; k++) { lists[k] = malloc(N * 4); for (int i = 0; i < N; i++) if (label[i] == k + 1) lists[k][n[k]++] = i; }
+    int prune = argc > 5 ? atoi(argv[5]) : 0;
+    if (prune) {
+        uint8_t* hopeful = malloc(N); for (int i = 0; i < N; i++) hopeful[i] = label[i] != 0;
+        long peel_evals = 0; int iters = 0, changed = 1;
+        while (changed) { changed = 0; iters++;
+            for (int i = 0; i < N; i++) if (hopeful[i]) { int y = i / W, x = i % W; arm_t a = arms[i]; int pot = 0; peel_evals++;
+                for (int t = -a.t; t <= a.b; t++) { int ri = (y + t) * W + x; arm_t a2 = arms[ri]; for (int q = -a2.l; q <= a2.r; q++) pot += (prune == 1) ? 1 : ((!isinf(d_old[ri + q])) || hopeful[ri + q]); }
+                if (pot <= ts) { hopeful[i] = 0; changed = 1; } }
+            if (prune == 1) break; }
+        int kept[2] = {0, 0};
+        for (int k = 0; k < 2; k++) { int m = 0; for (int i = 0; i < n[k]; i++) if (hopeful[lists[k][i]]) lists[k][m++] = lists[k][i]; kept[k] = m; }
+        printf("prune mode %d: iters %d peel_evals %ld kept %d/%d %d/%d\n", prune, iters, peel_evals, kept[0], n[0], kept[1], n[1]);
+        n[0] = kept[0]; n[1] = kept[1]; }
     int tw = (W + TILE - 1) / TILE, thh = (H + TILE - 1) / TILE;
     int* stamp = calloc(tw * thh, 4); int* evalep = calloc(N, 4); int epoch = 1; int reach = 34;
-    long rounds = 0; long checks = 0;
-    float* snap = malloc(N * 4);
+    long rounds = 0; long checks = 0; long skipped_slack = 0;
+    int* chg = calloc(tw * thh, 4); int* need = calloc(N, 4); int* snap = calloc(N, 4);
+    #define BOXSUM(x,y) ({ int _s=0; for (int ty = (y - reach < 0 ? 0 : (y - reach) / TILE); ty <= (y + reach) / TILE && ty < thh; ty++) for (int tx = (x - reach < 0 ? 0 : (x - reach) / TILE); tx <= (x + reach) / TILE && tx < tw; tx++) _s += chg[ty*tw+tx]; _s; })
+
     for (int it = 0; it < 5; it++) for (int k = 0; k < 2; k++) {
         int* L = lists[k]; int cnt = n[k]; if (!cnt) continue;
         int sweep_rounds = 0; long e0 = evals;
@@ -54,12 +70,18 @@ int main(int argc, char** argv) {
                 for (int i = g0; i < g1; i++) {
                     int p = L[i]; int y = p / W, x = p % W; checks++;
                     doit[i - g0] = (mode == 0) || stamp[(y / TILE) * tw + x / TILE] >= evalep[p];
-                    if (doit[i - g0]) res[i - g0] = vote(p, d_new, d_old);
+                    if (doit[i - g0] && mode == 2 && isinf(d_new[p]) && need[p] > 0) {
+                        int cur = BOXSUM(x, y);
+                        if (cur - snap[p] < need[p]) { doit[i - g0] = 0; skipped_slack++; }
+                    }
+                    if (doit[i - g0]) { res[i - g0] = vote(p, d_new, d_old);
+                        int nt = last_total <= ts ? ts + 1 - last_total : 0; float fr = th * last_total - last_peak; int nr = fr > 0 ? (int)floorf(fr) : 0;
+                        need[p] = nt > nr ? nt : nr; if (need[p] < 1) need[p] = 1; snap[p] = BOXSUM(x, y); }
                 }
                 for (int i = g0; i < g1; i++) if (doit[i - g0]) {
                     int p = L[i]; int y = p / W, x = p % W; evalep[p] = epoch;
                     float r = res[i - g0];
-                    if (memcmp(&r, &d_new[p], 4)) { d_new[p] = r; changed = 1;
+                    if (memcmp(&r, &d_new[p], 4)) { d_new[p] = r; changed = 1; chg[(y / TILE) * tw + x / TILE]++;
                         for (int ty = (y - reach < 0 ? 0 : (y - reach) / TILE); ty <= (y + reach) / TILE && ty < thh; ty++)
                             for (int tx = (x - reach < 0 ? 0 : (x - reach) / TILE); tx <= (x + reach) / TILE && tx < tw; tx++) stamp[ty * tw + tx] = epoch; }
                 }
@@ -68,7 +90,7 @@ int main(int argc, char** argv) {
             if (!changed) break;
         }
         int keep = 0;
-        for (int i = 0; i < cnt; i++) { int p = L[i]; if (!isinf(d_new[p])) { d_old[p] = d_new[p]; int y = p / W, x = p % W;
+        for (int i = 0; i < cnt; i++) { int p = L[i]; if (!isinf(d_new[p])) { d_old[p] = d_new[p]; int y = p / W, x = p % W; chg[(y / TILE) * tw + x / TILE]++;
                 for (int ty = (y - reach < 0 ? 0 : (y - reach) / TILE); ty <= (y + reach) / TILE && ty < thh; ty++)
                     for (int tx = (x - reach < 0 ? 0 : (x - reach) / TILE); tx <= (x + reach) / TILE && tx < tw; tx++) stamp[ty * tw + tx] = epoch; }
             else L[keep++] = p; }
@@ -76,7 +98,7 @@ int main(int argc, char** argv) {
         printf("it %d k %d: pending %d -> %d, rounds %d, evals %ld\n", it, k, cnt, keep, sweep_rounds, evals - e0);
         n[k] = keep;
     }
-    printf("TOTAL rounds %ld evals %ld checks %ld\n", rounds, evals, checks);
+    printf("TOTAL rounds %ld evals %ld checks %ld slack-skips %ld\n", rounds, evals, checks, skipped_slack);
     FILE* o = fopen(argv[1], "ab"); fclose(o);
     /* checksum of result */
     unsigned long long cs = 0; for (int i = 0; i < N; i++) { uint32_t u; memcpy(&u, &d_old[i], 4); cs = cs * 1000003ull + u; }
