@@ -500,28 +500,47 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                             ar[j] = (unsigned)v.x | ((unsigned)v.y << 8);
                         }
                         const int grp = lane >> 3, sub = lane & 7;
-                        for (int ri0 = 0; ri0 < rows; ri0 += 4) {
-                            const int ri = ri0 + grp;
-                            unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
-                            if (rows > 32) {
-                                const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31);
-                                const unsigned a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
-                                a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
-                            }
+                        // rows 0..31, first 16 columns of each: all loads are issued before any is consumed
+                        // (one memory round trip for the bulk of the region instead of one per group of 4 rows)
+                        int dv[8][2];
+                        bool more = rows > 32;
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int ri = 4 * i + grp;
+                            const unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri);
+                            dv[i][0] = dv[i][1] = 255;
                             if (ri < rows) {
                                 const int t = ri - top;
                                 const int rowi = rbase + ri * W;
                                 const int s_lo = -(int)(a2 & 255u), s_hi = (int)(a2 >> 8);
                                 const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);   // first s that reads OLD
                                 const int s0 = s_lo + sub, s1 = s0 + 8;
-                                int d0 = 255, d1 = 255;
-                                if (s0 <= s_hi) d0 = s0 < s_mid ? __ldcg(q_new + rowi + s0) : __ldcg(q_old + rowi + s0);
-                                if (s1 <= s_hi) d1 = s1 < s_mid ? __ldcg(q_new + rowi + s1) : __ldcg(q_old + rowi + s1);
-                                if (d0 < 254) atomicAdd(&hist[d0], 1);
-                                if (d1 < 254) atomicAdd(&hist[d1], 1);
-                                for (int sx = s1 + 8; sx <= s_hi; sx += 8) {
-                                    const int dv = sx < s_mid ? __ldcg(q_new + rowi + sx) : __ldcg(q_old + rowi + sx);
-                                    if (dv < 254) atomicAdd(&hist[dv], 1);
+                                if (s0 <= s_hi) dv[i][0] = s0 < s_mid ? __ldcg(q_new + rowi + s0) : __ldcg(q_old + rowi + s0);
+                                if (s1 <= s_hi) dv[i][1] = s1 < s_mid ? __ldcg(q_new + rowi + s1) : __ldcg(q_old + rowi + s1);
+                                more |= (s_hi - s_lo) >= 16;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            if (dv[i][0] < 254) atomicAdd(&hist[dv[i][0]], 1);
+                            if (dv[i][1] < 254) atomicAdd(&hist[dv[i][1]], 1);
+                        }
+                        if (__any_sync(0xffffffffu, more)) {   // rare: arms longer than 15 or more than 32 rows
+                            for (int ri0 = 0; ri0 < rows; ri0 += 4) {
+                                const int ri = ri0 + grp;
+                                unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
+                                const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31);
+                                const unsigned a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
+                                a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
+                                if (ri < rows) {
+                                    const int t = ri - top;
+                                    const int rowi = rbase + ri * W;
+                                    const int s_lo = -(int)(a2 & 255u), s_hi = (int)(a2 >> 8);
+                                    const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);
+                                    for (int sx = s_lo + sub + (ri < 32 ? 16 : 0); sx <= s_hi; sx += 8) {
+                                        const int d = sx < s_mid ? __ldcg(q_new + rowi + sx) : __ldcg(q_old + rowi + sx);
+                                        if (d < 254) atomicAdd(&hist[d], 1);
+                                    }
                                 }
                             }
                         }
