@@ -225,9 +225,13 @@ __device__ int rv_compact_invalid(int n, int* list, const float* d_old, int* s_w
     return base;
 }
 
-__device__ __forceinline__ void rv_stamp_tiles(int* tiles, int tw, int th, int x, int y, int reach, int epoch, int lane) {
+// `reach_up`: how far above (x,y) dependants can sit.  At commit time that is `reach` (everybody around sees
+// the new OLD value); during the rounds of a sweep it is 0: a changed NEW value is only read by pixels that
+// come LATER in raster order, and every pixel of a tile row above (x,y)'s own comes earlier.
+__device__ __forceinline__ void rv_stamp_tiles(int* tiles, int tw, int th, int x, int y, int reach, int epoch, int lane,
+                                               int reach_up) {
     const int tx0 = max(0, (x - reach) / RV_TILE), tx1 = min(tw - 1, (x + reach) / RV_TILE);
-    const int ty0 = max(0, (y - reach) / RV_TILE), ty1 = min(th - 1, (y + reach) / RV_TILE);
+    const int ty0 = max(0, (y - reach_up) / RV_TILE), ty1 = min(th - 1, (y + reach) / RV_TILE);
     const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
     for (int i = lane; i < nt; i += 32) __stcg(tiles + (ty0 + i / nx) * tw + tx0 + i % nx, epoch);
 }
@@ -335,7 +339,7 @@ k_region_voting_global(AdcParams P, const uchar4* __restrict__ arms, float* disp
                         __stcg(evalep + p, epoch);
                         if (changed) __stcg(d_new + p, r);
                     }
-                    if (changed) { rv_stamp_tiles(tiles, tw, th, x, y, reach, epoch, lane); warp_changed = true; }
+                    if (changed) { rv_stamp_tiles(tiles, tw, th, x, y, reach, epoch, lane, 0); warp_changed = true; }
                 }
                 if (warp_changed && lane == 0) __stcg(cnt + 4 + rnd % 3, 1);
                 cluster_sync_all();
@@ -355,7 +359,7 @@ k_region_voting_global(AdcParams P, const uchar4* __restrict__ arms, float* disp
                 if (v != ADC_INVALID_F) {
                     if (lane == 0) { __stcg(d_old + p, v); lab[p] = 0; }
                     const int y = p / W;
-                    rv_stamp_tiles(tiles, tw, th, p - y * W, y, reach, epoch, lane);
+                    rv_stamp_tiles(tiles, tw, th, p - y * W, y, reach, epoch, lane, reach);
                 }
             }
             epoch++;
@@ -500,32 +504,41 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                             ar[j] = (unsigned)v.x | ((unsigned)v.y << 8);
                         }
                         const int grp = lane >> 3, sub = lane & 7;
-                        // rows 0..31, first 16 columns of each: all loads are issued before any is consumed
-                        // (one memory round trip for the bulk of the region instead of one per group of 4 rows)
-                        int dv[8][2];
-                        bool more = rows > 32;
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
+                        // 4 rows x (2 x 8) columns of the region per trip, software-pipelined: the loads of trip i+1
+                        // are in flight while trip i is added to the histogram.  Trip count = ceil(rows/4), not a
+                        // fixed maximum, so small regions cost few instructions.
+                        const int n_rg = (rows + 3) >> 2;
+                        bool more = false;
+                        int d0 = 255, d1 = 255;
+                        auto fetch_rows = [&](int i, int& o0, int& o1) {
                             const int ri = 4 * i + grp;
-                            const unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri);
-                            dv[i][0] = dv[i][1] = 255;
+                            unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
+                            if (rows > 32) {
+                                const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31);
+                                const unsigned a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
+                                a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
+                            }
+                            o0 = o1 = 255;
                             if (ri < rows) {
                                 const int t = ri - top;
                                 const int rowi = rbase + ri * W;
                                 const int s_lo = -(int)(a2 & 255u), s_hi = (int)(a2 >> 8);
                                 const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);   // first s that reads OLD
                                 const int s0 = s_lo + sub, s1 = s0 + 8;
-                                if (s0 <= s_hi) dv[i][0] = s0 < s_mid ? __ldcg(q_new + rowi + s0) : __ldcg(q_old + rowi + s0);
-                                if (s1 <= s_hi) dv[i][1] = s1 < s_mid ? __ldcg(q_new + rowi + s1) : __ldcg(q_old + rowi + s1);
+                                if (s0 <= s_hi) o0 = s0 < s_mid ? __ldcg(q_new + rowi + s0) : __ldcg(q_old + rowi + s0);
+                                if (s1 <= s_hi) o1 = s1 < s_mid ? __ldcg(q_new + rowi + s1) : __ldcg(q_old + rowi + s1);
                                 more |= (s_hi - s_lo) >= 16;
                             }
+                        };
+                        fetch_rows(0, d0, d1);
+                        for (int i = 0; i < n_rg; i++) {
+                            int n0 = 255, n1 = 255;
+                            if (i + 1 < n_rg) fetch_rows(i + 1, n0, n1);
+                            if (d0 < 254) atomicAdd(&hist[d0], 1);
+                            if (d1 < 254) atomicAdd(&hist[d1], 1);
+                            d0 = n0; d1 = n1;
                         }
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            if (dv[i][0] < 254) atomicAdd(&hist[dv[i][0]], 1);
-                            if (dv[i][1] < 254) atomicAdd(&hist[dv[i][1]], 1);
-                        }
-                        if (__any_sync(0xffffffffu, more)) {   // rare: arms longer than 15 or more than 32 rows
+                        if (__any_sync(0xffffffffu, more)) {   // rare: a row segment longer than 16 pixels
                             for (int ri0 = 0; ri0 < rows; ri0 += 4) {
                                 const int ri = ri0 + grp;
                                 unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
@@ -537,7 +550,7 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                                     const int rowi = rbase + ri * W;
                                     const int s_lo = -(int)(a2 & 255u), s_hi = (int)(a2 >> 8);
                                     const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);
-                                    for (int sx = s_lo + sub + (ri < 32 ? 16 : 0); sx <= s_hi; sx += 8) {
+                                    for (int sx = s_lo + sub + 16; sx <= s_hi; sx += 8) {
                                         const int d = sx < s_mid ? __ldcg(q_new + rowi + sx) : __ldcg(q_old + rowi + sx);
                                         if (d < 254) atomicAdd(&hist[d], 1);
                                     }
@@ -564,7 +577,7 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                             __stcg(evalep + p, epoch);
                             if (changed) __stcg(q_new + p, (uint8_t)r);
                         }
-                        if (changed) { rv_stamp_tiles(tiles, tw, th, x, y, reach, epoch, lane); warp_changed = true; }
+                        if (changed) { rv_stamp_tiles(tiles, tw, th, x, y, reach, epoch, lane, 0); warp_changed = true; }
                     }
                 }
                 if (warp_changed && lane == 0) __stcg(cnt + 4 + rnd % 3, 1);
@@ -589,7 +602,7 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                         __stcg(lab + p, (uint8_t)0);
                     }
                     const int y = p / W;
-                    rv_stamp_tiles(tiles, tw, th, p - y * W, y, reach, epoch, lane);
+                    rv_stamp_tiles(tiles, tw, th, p - y * W, y, reach, epoch, lane, reach);
                 }
             }
             epoch++;
