@@ -452,7 +452,7 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
         const int* list = pend + ((size_t)pair * 2 + k) * dm.N;
         for (int i = gtid; i < n_list[k]; i += n_gthreads) __stcg(evalep + list[i], 0);
     }
-    if (gtid < 3) __stcg(cnt + 4 + gtid, 0);
+    if (gtid < 6) __stcg(cnt + 4 + gtid, 0);
     int epoch = 1, rnd = 0;
     cluster_sync_all();
 
@@ -463,14 +463,18 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
             if (n == 0) continue;  // uniform across the cluster
             bool any_fill = false;
             while (true) {
-                if (gtid == 0) __stcg(cnt + 4 + (rnd + 1) % 3, 0);
+                if (gtid == 0) { __stcg(cnt + 4 + (rnd + 1) % 3, 0); __stcg(cnt + 7 + (rnd + 1) % 3, 0); }
                 bool warp_changed = false;
                 // 32 list entries per warp trip: every lane checks one pending pixel (is its tile stamped since
                 // its last evaluation?), then the warp evaluates the dirty ones one after the other
-                // (entries are dealt so that neighbouring list entries -- neighbouring pixels, which tend to be
-                //  dirty together -- go to different warps: entry = trip*32*n_gwarps + lane*n_gwarps + gwarp)
-                for (int base = 0; base < n; base += n_gwarps * 32) {
-                    const int my = base + lane * n_gwarps + gwarp;
+                // warps pull chunks of 32 list entries from a per-round cluster-wide counter, so that a round ends
+                // when the work is done, not when the unluckiest statically assigned warp is
+                while (true) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(cnt + 7 + rnd % 3, 32);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base >= n) break;
+                    const int my = base + lane;
                     int p_l = 0;
                     unsigned tb_l = 0;
                     bool dirty_l = false;
@@ -590,17 +594,22 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                 any_fill = true;
             }
             if (!any_fill) continue;
-            for (int idx = gwarp; idx < n; idx += n_gwarps) {
-                const int p = __ldcg(list + idx);
-                const int v = __ldcg(q_new + p);
-                if (v != 255) {
-                    if (lane == 0) {
-                        const float f = (float)(v + dm.dmin);
-                        __stcg(q_old + p, (uint8_t)v);
-                        __stcg(d_old + p, f);
-                        __stcg(d_new + p, f);
-                        __stcg(lab + p, (uint8_t)0);
-                    }
+            for (int base = gwarp * 32; base < n; base += n_gwarps * 32) {   // one list entry per lane
+                const int my = base + lane;
+                int p_l = 0, v_l = 255;
+                if (my < n) { p_l = __ldcg(list + my); v_l = __ldcg(q_new + p_l); }
+                if (v_l != 255) {
+                    const float f = (float)(v_l + dm.dmin);
+                    __stcg(q_old + p_l, (uint8_t)v_l);
+                    __stcg(d_old + p_l, f);
+                    __stcg(d_new + p_l, f);
+                    __stcg(lab + p_l, (uint8_t)0);
+                }
+                unsigned filled = __ballot_sync(0xffffffffu, v_l != 255);
+                while (filled) {
+                    const int src = __ffs(filled) - 1;
+                    filled &= filled - 1;
+                    const int p = __shfl_sync(0xffffffffu, p_l, src);
                     const int y = p / W;
                     rv_stamp_tiles(tiles, tw, th, p - y * W, y, reach, epoch, lane, reach);
                 }
