@@ -78,6 +78,7 @@ struct AdcWave {            // device pointers of one wave (S pairs)
     int* tile_stamp;        // [S][tiles] region voting: epoch of the last change near a 16x16 tile
     int* last_eval;         // [S][N]     region voting: epoch of a pixel's (or tile's) last evaluation
     unsigned long long* wta_key;  // [S][N] right-view WTA keys (ordered cost << 32 | disparity index)
+    int2* vote_dirty;       // [S][N]     region voting: work list of the current round
     uchar2* vote_alr;       // [S][N]     region voting: horizontal arms only (left, right)
     uint8_t* vote_dq;       // [S][2][N]  region voting: rounded disparity index per pixel, NEW and OLD state
     const float* lut_ad;    // [766]  (1 - exp(-(s/3)/lambda_ad)) + 1, host libm expf

@@ -421,7 +421,7 @@ __global__ void k_vote_encode(AdcDims dm, const float* __restrict__ disp, const 
 __global__ void __cluster_dims__(RV_CLUSTER, 1, 1) __launch_bounds__(RV_THREADS)
 k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restrict__ alr_all,
                       float* disp_old, float* disp_new, uint8_t* dq, uint8_t* label, int* pend, int* counters,
-                      int* tile_stamp, int* last_eval) {
+                      int* tile_stamp, int* last_eval, int2* dirty_all) {
     __shared__ int s_hist[RV_WARPS][RV_MAXD];
     __shared__ int s_tot[RV_WARPS];
     const AdcDims& dm = P.dm;
@@ -442,6 +442,7 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
     uint8_t* lab = label + (size_t)pair * dm.N;
     int* tiles = tile_stamp + (size_t)pair * tw * th;
     int* evalep = last_eval + (size_t)pair * dm.N;
+    int2* dlist = dirty_all + (size_t)pair * dm.N;   // this round's dirty pixels: (pixel index, top | bottom<<8)
     int* cnt = counters + pair * ADC_CNT;
     int n_list[2] = {__ldcg(cnt + 10), __ldcg(cnt + 11)};   // active (fillable) lists, see launch_active_lists
     int rounds_total = 0, evals = 0;
@@ -465,15 +466,9 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
             while (true) {
                 if (gtid == 0) { __stcg(cnt + 4 + (rnd + 1) % 3, 0); __stcg(cnt + 7 + (rnd + 1) % 3, 0); }
                 bool warp_changed = false;
-                // 32 list entries per warp trip: every lane checks one pending pixel (is its tile stamped since
-                // its last evaluation?), then the warp evaluates the dirty ones one after the other
-                // warps pull chunks of 32 list entries from a per-round cluster-wide counter, so that a round ends
-                // when the work is done, not when the unluckiest statically assigned warp is
-                while (true) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(cnt + 7 + rnd % 3, 32);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (base >= n) break;
+                // ---- phase A: every lane tests one list entry (is its tile stamped since its last evaluation?);
+                //      the dirty ones are appended to this round's work list
+                for (int base = gwarp * 32; base < n; base += n_gwarps * 32) {
                     const int my = base + lane;
                     int p_l = 0;
                     unsigned tb_l = 0;
@@ -485,104 +480,114 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                         tb_l = (unsigned)a_l.z | ((unsigned)a_l.w << 8);
                         dirty_l = __ldcg(tiles + (yy / RV_TILE) * tw + xx / RV_TILE) >= __ldcg(evalep + p_l);
                     }
-                    unsigned todo = __ballot_sync(0xffffffffu, dirty_l);
-                    while (todo) {
-                        const int src = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const int p = __shfl_sync(0xffffffffu, p_l, src);
-                        const unsigned tb = __shfl_sync(0xffffffffu, tb_l, src);
-                        const int y = p / W, x = p - y * W;
-                        evals++;
-                        for (int b = lane; b < D; b += 32) hist[b] = 0;
-                        __syncwarp();
-                        // Region scan: the horizontal arms of all (<= 69) region rows are fetched in ONE round of
-                        // loads, three per lane at most, and handed out by shuffle; then 4 rows x 8 columns of the
-                        // region are visited per trip (the first two 8-column chunks of a row are loaded together).
-                        const int top = (int)(tb & 255u), rows = top + (int)(tb >> 8) + 1;
-                        const int rbase = (y - top) * W + x;
-                        unsigned ar[3];
+                    const unsigned dm_ = __ballot_sync(0xffffffffu, dirty_l);
+                    if (dm_) {
+                        int off = 0;
+                        if (lane == 0) off = atomicAdd(cnt + 7 + rnd % 3, __popc(dm_));
+                        off = __shfl_sync(0xffffffffu, off, 0);
+                        if (dirty_l) dlist[off + __popc(dm_ & ((1u << lane) - 1u))] = make_int2(p_l, (int)tb_l);
+                    }
+                }
+                cluster_sync_all();
+                // ---- phase B: the dirty pixels, dealt evenly over all warps of the cluster (neighbouring pixels
+                //      are dirty together, so dealing out the unfiltered list would serialise them on a few warps)
+                const int n_dirty = __ldcg(cnt + 7 + rnd % 3);
+                for (int idx = gwarp; idx < n_dirty; idx += n_gwarps) {
+                    const int2 ent = __ldcg(dlist + idx);
+                    const int p = ent.x;
+                    const unsigned tb = (unsigned)ent.y;
+                    const int y = p / W, x = p - y * W;
+                    evals++;
+                    for (int b = lane; b < D; b += 32) hist[b] = 0;
+                    __syncwarp();
+                    // Region scan: the horizontal arms of all (<= 69) region rows are fetched in ONE round of
+                    // loads, three per lane at most, and handed out by shuffle; then 4 rows x 8 columns of the
+                    // region are visited per trip (the first two 8-column chunks of a row are loaded together).
+                    const int top = (int)(tb & 255u), rows = top + (int)(tb >> 8) + 1;
+                    const int rbase = (y - top) * W + x;
+                    unsigned ar[3];
 #pragma unroll
-                        for (int j = 0; j < 3; j++) {
-                            const int ri = lane + 32 * j;
-                            const uchar2 v = ri < rows ? __ldg(ALR + rbase + ri * W) : make_uchar2(0, 0);
-                            ar[j] = (unsigned)v.x | ((unsigned)v.y << 8);
+                    for (int j = 0; j < 3; j++) {
+                        const int ri = lane + 32 * j;
+                        const uchar2 v = ri < rows ? __ldg(ALR + rbase + ri * W) : make_uchar2(0, 0);
+                        ar[j] = (unsigned)v.x | ((unsigned)v.y << 8);
+                    }
+                    const int grp = lane >> 3, sub = lane & 7;
+                    // 4 rows x (2 x 8) columns of the region per trip, software-pipelined: the loads of trip i+1
+                    // are in flight while trip i is added to the histogram.  Trip count = ceil(rows/4), not a
+                    // fixed maximum, so small regions cost few instructions.
+                    const int n_rg = (rows + 3) >> 2;
+                    bool more = false;
+                    int d0 = 255, d1 = 255;
+                    auto fetch_rows = [&](int i, int& o0, int& o1) {
+                        const int ri = 4 * i + grp;
+                        unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
+                        if (rows > 32) {
+                            const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31);
+                            const unsigned a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
+                            a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
                         }
-                        const int grp = lane >> 3, sub = lane & 7;
-                        // 4 rows x (2 x 8) columns of the region per trip, software-pipelined: the loads of trip i+1
-                        // are in flight while trip i is added to the histogram.  Trip count = ceil(rows/4), not a
-                        // fixed maximum, so small regions cost few instructions.
-                        const int n_rg = (rows + 3) >> 2;
-                        bool more = false;
-                        int d0 = 255, d1 = 255;
-                        auto fetch_rows = [&](int i, int& o0, int& o1) {
-                            const int ri = 4 * i + grp;
+                        o0 = o1 = 255;
+                        if (ri < rows) {
+                            const int t = ri - top;
+                            const int rowi = rbase + ri * W;
+                            const int s_lo = -(int)(a2 & 255u), s_hi = (int)(a2 >> 8);
+                            const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);   // first s that reads OLD
+                            const int s0 = s_lo + sub, s1 = s0 + 8;
+                            if (s0 <= s_hi) o0 = s0 < s_mid ? __ldcg(q_new + rowi + s0) : __ldcg(q_old + rowi + s0);
+                            if (s1 <= s_hi) o1 = s1 < s_mid ? __ldcg(q_new + rowi + s1) : __ldcg(q_old + rowi + s1);
+                            more |= (s_hi - s_lo) >= 16;
+                        }
+                    };
+                    fetch_rows(0, d0, d1);
+                    for (int i = 0; i < n_rg; i++) {
+                        int n0 = 255, n1 = 255;
+                        if (i + 1 < n_rg) fetch_rows(i + 1, n0, n1);
+                        if (d0 < 254) atomicAdd(&hist[d0], 1);
+                        if (d1 < 254) atomicAdd(&hist[d1], 1);
+                        d0 = n0; d1 = n1;
+                    }
+                    if (__any_sync(0xffffffffu, more)) {   // rare: a row segment longer than 16 pixels
+                        for (int ri0 = 0; ri0 < rows; ri0 += 4) {
+                            const int ri = ri0 + grp;
                             unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
-                            if (rows > 32) {
-                                const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31);
-                                const unsigned a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
-                                a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
-                            }
-                            o0 = o1 = 255;
+                            const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31);
+                            const unsigned a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
+                            a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
                             if (ri < rows) {
                                 const int t = ri - top;
                                 const int rowi = rbase + ri * W;
                                 const int s_lo = -(int)(a2 & 255u), s_hi = (int)(a2 >> 8);
-                                const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);   // first s that reads OLD
-                                const int s0 = s_lo + sub, s1 = s0 + 8;
-                                if (s0 <= s_hi) o0 = s0 < s_mid ? __ldcg(q_new + rowi + s0) : __ldcg(q_old + rowi + s0);
-                                if (s1 <= s_hi) o1 = s1 < s_mid ? __ldcg(q_new + rowi + s1) : __ldcg(q_old + rowi + s1);
-                                more |= (s_hi - s_lo) >= 16;
-                            }
-                        };
-                        fetch_rows(0, d0, d1);
-                        for (int i = 0; i < n_rg; i++) {
-                            int n0 = 255, n1 = 255;
-                            if (i + 1 < n_rg) fetch_rows(i + 1, n0, n1);
-                            if (d0 < 254) atomicAdd(&hist[d0], 1);
-                            if (d1 < 254) atomicAdd(&hist[d1], 1);
-                            d0 = n0; d1 = n1;
-                        }
-                        if (__any_sync(0xffffffffu, more)) {   // rare: a row segment longer than 16 pixels
-                            for (int ri0 = 0; ri0 < rows; ri0 += 4) {
-                                const int ri = ri0 + grp;
-                                unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
-                                const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31);
-                                const unsigned a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
-                                a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
-                                if (ri < rows) {
-                                    const int t = ri - top;
-                                    const int rowi = rbase + ri * W;
-                                    const int s_lo = -(int)(a2 & 255u), s_hi = (int)(a2 >> 8);
-                                    const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);
-                                    for (int sx = s_lo + sub + 16; sx <= s_hi; sx += 8) {
-                                        const int d = sx < s_mid ? __ldcg(q_new + rowi + sx) : __ldcg(q_old + rowi + sx);
-                                        if (d < 254) atomicAdd(&hist[d], 1);
-                                    }
+                                const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);
+                                for (int sx = s_lo + sub + 16; sx <= s_hi; sx += 8) {
+                                    const int d = sx < s_mid ? __ldcg(q_new + rowi + sx) : __ldcg(q_old + rowi + sx);
+                                    if (d < 254) atomicAdd(&hist[d], 1);
                                 }
                             }
                         }
-                        __syncwarp();
-                        int peak = 0, best = 0x7fffffff, total = 0;
-                        for (int b = lane; b < D; b += 32) {
-                            const int h = hist[b];
-                            if (peak < h) { peak = h; best = b; }
-                            total += h;
-                        }
-                        const int gpeak = __reduce_max_sync(0xffffffffu, peak);
-                        const int gbest = __reduce_min_sync(0xffffffffu, peak == gpeak ? best : 0x7fffffff);
-                        total = __reduce_add_sync(0xffffffffu, total);
-                        int r = 255;
-                        if (gpeak > 0 && total > P.irv_ts &&
-                            __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th)
-                            r = gbest;
-                        const bool changed = r != (int)__ldcg(q_new + p);
-                        __syncwarp();
-                        if (lane == 0) {
-                            __stcg(evalep + p, epoch);
-                            if (changed) __stcg(q_new + p, (uint8_t)r);
-                        }
-                        if (changed) { rv_stamp_tiles(tiles, tw, th, x, y, reach, epoch, lane, 0); warp_changed = true; }
                     }
+                    __syncwarp();
+                    int peak = 0, best = 0x7fffffff, total = 0;
+                    for (int b = lane; b < D; b += 32) {
+                        const int h = hist[b];
+                        if (peak < h) { peak = h; best = b; }
+                        total += h;
+                    }
+                    const int gpeak = __reduce_max_sync(0xffffffffu, peak);
+                    const int gbest = __reduce_min_sync(0xffffffffu, peak == gpeak ? best : 0x7fffffff);
+                    total = __reduce_add_sync(0xffffffffu, total);
+                    int r = 255;
+                    if (gpeak > 0 && total > P.irv_ts &&
+                        __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th)
+                        r = gbest;
+                    const bool changed = r != (int)__ldcg(q_new + p);
+                    __syncwarp();
+                    if (lane == 0) {
+                        __stcg(evalep + p, epoch);
+                        if (changed) __stcg(q_new + p, (uint8_t)r);
+                    }
+                    if (changed) { rv_stamp_tiles(tiles, tw, th, x, y, reach, epoch, lane, 0); warp_changed = true; }
+
                 }
                 if (warp_changed && lane == 0) __stcg(cnt + 4 + rnd % 3, 1);
                 cluster_sync_all();
@@ -835,7 +840,7 @@ void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, un
         launch_active_lists(P, w, st, launches);
         k_vote_encode<<<egrid, 256, 0, st>>>(P.dm, w.disp_l, w.arms, w.vote_dq, w.vote_alr);
         k_region_voting_bytes<<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.vote_alr, w.disp_l, w.disp_t, w.vote_dq,
-                                                                      w.label, w.vlist, w.counters, w.tile_stamp, w.last_eval);
+                                                                      w.label, w.vlist, w.counters, w.tile_stamp, w.last_eval, w.vote_dirty);
         *launches += 2;
         adc_launch_build_lists(P, w, st, launches);   // outlier lists = every listed pixel that is still invalid
     } else if (mode == 0 && P.dm.D <= 254 && reach <= RV_MAXREACH) {
