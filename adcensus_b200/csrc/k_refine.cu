@@ -378,22 +378,11 @@ k_region_voting_global(AdcParams P, const uchar4* __restrict__ arms, float* disp
 }
 
 // ---------------------------------------------------------------------------------------------
-// Shared-memory tile version of the same fixed point (the fast path).  Only the rounded
-// disparity index matters for a vote, so the state is kept as one byte per pixel (0..253 = index,
-// 254 = valid but outside [0,D), 255 = invalid) in two global byte maps (OLD/NEW).  The image is
-// cut into 64x64 tiles; in every round the CTAs of the cluster pull *active* tiles (stamped since
-// their last evaluation) from a queue, stage the tile plus a halo of `reach` pixels -- state bytes
-// and horizontal arms -- into shared memory with coalesced loads, and iterate the tile's pending
-// pixels to a local fixed point entirely out of shared memory (~30-cycle accesses instead of
-// dependent L2 round trips).  Changes are written through to the global NEW map and stamp the
-// neighbouring tiles; the rounds end when a whole round changes nothing, exactly as above.
+// Byte state for the fast voting kernel: only the rounded disparity index matters for a vote, so the
+// state is one byte per pixel (0..253 = index, 254 = valid but outside [0,D), 255 = invalid).
 // ---------------------------------------------------------------------------------------------
-#define RV_T 64
-#define RV_MAXREACH 34
-#define RV_INNER 4
-
 __global__ void k_vote_encode(AdcDims dm, const float* __restrict__ disp, const uchar4* __restrict__ arms,
-                              uint8_t* __restrict__ dq, uchar2* __restrict__ alr) {
+                              uint8_t* __restrict__ dq, uchar2* __restrict__ alr) {   // dq: [2i] = NEW, [2i+1] = OLD
     const int pair = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dm.N) return;
@@ -403,8 +392,7 @@ __global__ void k_vote_encode(AdcDims dm, const float* __restrict__ disp, const 
         const int di = (int)roundf(d) - dm.dmin;
         v = (di >= 0 && di < dm.D && di < 254) ? (uint8_t)di : (uint8_t)254;
     }
-    dq[((size_t)pair * 2 + 0) * dm.N + i] = v;
-    dq[((size_t)pair * 2 + 1) * dm.N + i] = v;
+    reinterpret_cast<uchar2*>(dq + (size_t)pair * 2 * dm.N)[i] = make_uchar2(v, v);
     const uchar4 a = arms[(size_t)pair * dm.N + i];
     alr[(size_t)pair * dm.N + i] = make_uchar2(a.x, a.y);   // horizontal arms, 2 bytes per pixel
 }
@@ -421,7 +409,7 @@ __global__ void k_vote_encode(AdcDims dm, const float* __restrict__ disp, const 
 __global__ void __cluster_dims__(RV_CLUSTER, 1, 1) __launch_bounds__(RV_THREADS)
 k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restrict__ alr_all,
                       float* disp_old, float* disp_new, uint8_t* dq, uint8_t* label, int* pend, int* counters,
-                      int* tile_stamp, int* last_eval, int2* dirty_all) {
+                      int* tile_stamp, int* last_eval) {
     __shared__ int s_hist[RV_WARPS][RV_MAXD];
     __shared__ int s_tot[RV_WARPS];
     const AdcDims& dm = P.dm;
@@ -437,12 +425,11 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
     const uchar2* ALR = alr_all + (size_t)pair * dm.N;
     float* d_old = disp_old + (size_t)pair * dm.N;
     float* d_new = disp_new + (size_t)pair * dm.N;
-    uint8_t* q_new = dq + ((size_t)pair * 2 + 0) * dm.N;
-    uint8_t* q_old = dq + ((size_t)pair * 2 + 1) * dm.N;
+    uint8_t* q2 = dq + (size_t)pair * 2 * dm.N;        // per pixel two bytes: [2p] = NEW state, [2p+1] = OLD state
+    const unsigned short* q2w = reinterpret_cast<const unsigned short*>(q2);
     uint8_t* lab = label + (size_t)pair * dm.N;
     int* tiles = tile_stamp + (size_t)pair * tw * th;
     int* evalep = last_eval + (size_t)pair * dm.N;
-    int2* dlist = dirty_all + (size_t)pair * dm.N;   // this round's dirty pixels: (pixel index, top | bottom<<8)
     int* cnt = counters + pair * ADC_CNT;
     int n_list[2] = {__ldcg(cnt + 10), __ldcg(cnt + 11)};   // active (fillable) lists, see launch_active_lists
     int rounds_total = 0, evals = 0;
@@ -453,7 +440,7 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
         const int* list = pend + ((size_t)pair * 2 + k) * dm.N;
         for (int i = gtid; i < n_list[k]; i += n_gthreads) __stcg(evalep + list[i], 0);
     }
-    if (gtid < 6) __stcg(cnt + 4 + gtid, 0);
+    if (gtid < 3) __stcg(cnt + 4 + gtid, 0);
     int epoch = 1, rnd = 0;
     cluster_sync_all();
 
@@ -464,12 +451,14 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
             if (n == 0) continue;  // uniform across the cluster
             bool any_fill = false;
             while (true) {
-                if (gtid == 0) { __stcg(cnt + 4 + (rnd + 1) % 3, 0); __stcg(cnt + 7 + (rnd + 1) % 3, 0); }
+                if (gtid == 0) __stcg(cnt + 4 + (rnd + 1) % 3, 0);
                 bool warp_changed = false;
-                // ---- phase A: every lane tests one list entry (is its tile stamped since its last evaluation?);
-                //      the dirty ones are appended to this round's work list
-                for (int base = gwarp * 32; base < n; base += n_gwarps * 32) {
-                    const int my = base + lane;
+                // 32 list entries per warp trip: every lane checks one pending pixel (is its tile stamped since
+                // its last evaluation?), then the warp evaluates the dirty ones one after the other
+                // (entries are dealt so that neighbouring list entries -- neighbouring pixels, which tend to be
+                //  dirty together -- go to different warps: entry = trip*32*n_gwarps + lane*n_gwarps + gwarp)
+                for (int base = 0; base < n; base += n_gwarps * 32) {
+                    const int my = base + lane * n_gwarps + gwarp;
                     int p_l = 0;
                     unsigned tb_l = 0;
                     bool dirty_l = false;
@@ -480,114 +469,89 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                         tb_l = (unsigned)a_l.z | ((unsigned)a_l.w << 8);
                         dirty_l = __ldcg(tiles + (yy / RV_TILE) * tw + xx / RV_TILE) >= __ldcg(evalep + p_l);
                     }
-                    const unsigned dm_ = __ballot_sync(0xffffffffu, dirty_l);
-                    if (dm_) {
-                        int off = 0;
-                        if (lane == 0) off = atomicAdd(cnt + 7 + rnd % 3, __popc(dm_));
-                        off = __shfl_sync(0xffffffffu, off, 0);
-                        if (dirty_l) dlist[off + __popc(dm_ & ((1u << lane) - 1u))] = make_int2(p_l, (int)tb_l);
-                    }
-                }
-                cluster_sync_all();
-                // ---- phase B: the dirty pixels, dealt evenly over all warps of the cluster (neighbouring pixels
-                //      are dirty together, so dealing out the unfiltered list would serialise them on a few warps)
-                const int n_dirty = __ldcg(cnt + 7 + rnd % 3);
-                for (int idx = gwarp; idx < n_dirty; idx += n_gwarps) {
-                    const int2 ent = __ldcg(dlist + idx);
-                    const int p = ent.x;
-                    const unsigned tb = (unsigned)ent.y;
-                    const int y = p / W, x = p - y * W;
-                    evals++;
-                    for (int b = lane; b < D; b += 32) hist[b] = 0;
-                    __syncwarp();
-                    // Region scan: the horizontal arms of all (<= 69) region rows are fetched in ONE round of
-                    // loads, three per lane at most, and handed out by shuffle; then 4 rows x 8 columns of the
-                    // region are visited per trip (the first two 8-column chunks of a row are loaded together).
-                    const int top = (int)(tb & 255u), rows = top + (int)(tb >> 8) + 1;
-                    const int rbase = (y - top) * W + x;
-                    unsigned ar[3];
-#pragma unroll
-                    for (int j = 0; j < 3; j++) {
-                        const int ri = lane + 32 * j;
-                        const uchar2 v = ri < rows ? __ldg(ALR + rbase + ri * W) : make_uchar2(0, 0);
-                        ar[j] = (unsigned)v.x | ((unsigned)v.y << 8);
-                    }
-                    const int grp = lane >> 3, sub = lane & 7;
-                    // 4 rows x (2 x 8) columns of the region per trip, software-pipelined: the loads of trip i+1
-                    // are in flight while trip i is added to the histogram.  Trip count = ceil(rows/4), not a
-                    // fixed maximum, so small regions cost few instructions.
-                    const int n_rg = (rows + 3) >> 2;
-                    bool more = false;
-                    int d0 = 255, d1 = 255;
-                    auto fetch_rows = [&](int i, int& o0, int& o1) {
-                        const int ri = 4 * i + grp;
-                        unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
+                    unsigned todo = __ballot_sync(0xffffffffu, dirty_l);
+                    while (todo) {
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const int p = __shfl_sync(0xffffffffu, p_l, src);
+                        const unsigned tb = __shfl_sync(0xffffffffu, tb_l, src);
+                        const int y = p / W, x = p - y * W;
+                        evals++;
+                        for (int b = lane; b < D; b += 32) hist[b] = 0;
+                        __syncwarp();
+                        // Region scan.  The horizontal arms of all (<= 69) region rows are fetched in ONE round of loads
+                        // (three per lane at most) and handed out by shuffle; then the region is visited in trips of
+                        // 4 rows x 16 columns, software-pipelined (the loads of trip j+1 are in flight while trip j is
+                        // added to the histogram).  Trip count = ceil(rows/4) x ceil(longest row/16): small regions cost
+                        // few instructions.  One 16-bit load brings a pixel's NEW and OLD state.
+                        const int top = (int)(tb & 255u), rows = top + (int)(tb >> 8) + 1;
+                        const int rbase = (y - top) * W + x;
+                        unsigned ar0, ar1 = 0, ar2 = 0;
+                        {
+                            const uchar2 v = lane < rows ? __ldg(ALR + rbase + lane * W) : make_uchar2(0, 0);
+                            ar0 = (unsigned)v.x | ((unsigned)v.y << 8);
+                        }
                         if (rows > 32) {
-                            const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31);
-                            const unsigned a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
-                            a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
+                            const uchar2 v1 = lane + 32 < rows ? __ldg(ALR + rbase + (lane + 32) * W) : make_uchar2(0, 0);
+                            const uchar2 v2 = lane + 64 < rows ? __ldg(ALR + rbase + (lane + 64) * W) : make_uchar2(0, 0);
+                            ar1 = (unsigned)v1.x | ((unsigned)v1.y << 8);
+                            ar2 = (unsigned)v2.x | ((unsigned)v2.y << 8);
                         }
-                        o0 = o1 = 255;
-                        if (ri < rows) {
-                            const int t = ri - top;
-                            const int rowi = rbase + ri * W;
-                            const int s_lo = -(int)(a2 & 255u), s_hi = (int)(a2 >> 8);
-                            const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);   // first s that reads OLD
-                            const int s0 = s_lo + sub, s1 = s0 + 8;
-                            if (s0 <= s_hi) o0 = s0 < s_mid ? __ldcg(q_new + rowi + s0) : __ldcg(q_old + rowi + s0);
-                            if (s1 <= s_hi) o1 = s1 < s_mid ? __ldcg(q_new + rowi + s1) : __ldcg(q_old + rowi + s1);
-                            more |= (s_hi - s_lo) >= 16;
-                        }
-                    };
-                    fetch_rows(0, d0, d1);
-                    for (int i = 0; i < n_rg; i++) {
-                        int n0 = 255, n1 = 255;
-                        if (i + 1 < n_rg) fetch_rows(i + 1, n0, n1);
-                        if (d0 < 254) atomicAdd(&hist[d0], 1);
-                        if (d1 < 254) atomicAdd(&hist[d1], 1);
-                        d0 = n0; d1 = n1;
-                    }
-                    if (__any_sync(0xffffffffu, more)) {   // rare: a row segment longer than 16 pixels
-                        for (int ri0 = 0; ri0 < rows; ri0 += 4) {
-                            const int ri = ri0 + grp;
-                            unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
-                            const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31);
-                            const unsigned a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
-                            a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
-                            if (ri < rows) {
-                                const int t = ri - top;
-                                const int rowi = rbase + ri * W;
-                                const int s_lo = -(int)(a2 & 255u), s_hi = (int)(a2 >> 8);
-                                const int s_mid = t < 0 ? s_hi + 1 : (t == 0 ? 0 : s_lo);
-                                for (int sx = s_lo + sub + 16; sx <= s_hi; sx += 8) {
-                                    const int d = sx < s_mid ? __ldcg(q_new + rowi + sx) : __ldcg(q_old + rowi + sx);
-                                    if (d < 254) atomicAdd(&hist[d], 1);
-                                }
+                        const int span_l = (int)(ar0 & 255u) + (int)(ar0 >> 8);
+                        const int span_m = max(span_l, max((int)(ar1 & 255u) + (int)(ar1 >> 8), (int)(ar2 & 255u) + (int)(ar2 >> 8)));
+                        const int ncp = (__reduce_max_sync(0xffffffffu, span_m) >> 4) + 1;   // 16-column chunks per row
+                        const int grp = lane >> 3, sub = lane & 7;
+                        const int n_trips = ((rows + 3) >> 2) * ncp;
+                        int ti = 0, tc = 0;                        // row group / column chunk of the trip being FETCHED
+                        auto fetch_trip = [&](int& o0, int& o1) {
+                            const int ri = 4 * ti + grp;
+                            unsigned a2 = __shfl_sync(0xffffffffu, ar0, ri & 31);
+                            if (rows > 32) {
+                                const unsigned a2b = __shfl_sync(0xffffffffu, ar1, ri & 31);
+                                const unsigned a2c = __shfl_sync(0xffffffffu, ar2, ri & 31);
+                                a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
                             }
+                            const int s_hi = ri < rows ? (int)(a2 >> 8) : -0x10000;       // dead rows: empty segment
+                            const int s0 = -(int)(a2 & 255u) + sub + 16 * tc, s1 = s0 + 8;
+                            const int t = ri - top;
+                            const int mid = t < 0 ? 0x10000 : (t == 0 ? 0 : -0x10000);   // columns below `mid` read NEW
+                            const unsigned short* rp = q2w + rbase + ri * W;
+                            o0 = o1 = 255;
+                            if (s0 <= s_hi) { const unsigned w2 = __ldcg(rp + s0); o0 = s0 < mid ? (int)(w2 & 255u) : (int)(w2 >> 8); }
+                            if (s1 <= s_hi) { const unsigned w2 = __ldcg(rp + s1); o1 = s1 < mid ? (int)(w2 & 255u) : (int)(w2 >> 8); }
+                            if (++tc == ncp) { tc = 0; ti++; }
+                        };
+                        int d0, d1;
+                        fetch_trip(d0, d1);
+                        for (int j = 0; j < n_trips; j++) {
+                            int n0 = 255, n1 = 255;
+                            if (j + 1 < n_trips) fetch_trip(n0, n1);
+                            if (d0 < 254) atomicAdd(&hist[d0], 1);
+                            if (d1 < 254) atomicAdd(&hist[d1], 1);
+                            d0 = n0; d1 = n1;
                         }
+                        __syncwarp();
+                        int peak = 0, best = 0x7fffffff, total = 0;
+                        for (int b = lane; b < D; b += 32) {
+                            const int h = hist[b];
+                            if (peak < h) { peak = h; best = b; }
+                            total += h;
+                        }
+                        const int gpeak = __reduce_max_sync(0xffffffffu, peak);
+                        const int gbest = __reduce_min_sync(0xffffffffu, peak == gpeak ? best : 0x7fffffff);
+                        total = __reduce_add_sync(0xffffffffu, total);
+                        int r = 255;
+                        if (gpeak > 0 && total > P.irv_ts &&
+                            __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th)
+                            r = gbest;
+                        const bool changed = r != (int)__ldcg(q2 + 2 * p);
+                        __syncwarp();
+                        if (lane == 0) {
+                            __stcg(evalep + p, epoch);
+                            if (changed) __stcg(q2 + 2 * p, (uint8_t)r);
+                        }
+                        if (changed) { rv_stamp_tiles(tiles, tw, th, x, y, reach, epoch, lane, 0); warp_changed = true; }
                     }
-                    __syncwarp();
-                    int peak = 0, best = 0x7fffffff, total = 0;
-                    for (int b = lane; b < D; b += 32) {
-                        const int h = hist[b];
-                        if (peak < h) { peak = h; best = b; }
-                        total += h;
-                    }
-                    const int gpeak = __reduce_max_sync(0xffffffffu, peak);
-                    const int gbest = __reduce_min_sync(0xffffffffu, peak == gpeak ? best : 0x7fffffff);
-                    total = __reduce_add_sync(0xffffffffu, total);
-                    int r = 255;
-                    if (gpeak > 0 && total > P.irv_ts &&
-                        __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th)
-                        r = gbest;
-                    const bool changed = r != (int)__ldcg(q_new + p);
-                    __syncwarp();
-                    if (lane == 0) {
-                        __stcg(evalep + p, epoch);
-                        if (changed) __stcg(q_new + p, (uint8_t)r);
-                    }
-                    if (changed) { rv_stamp_tiles(tiles, tw, th, x, y, reach, epoch, lane, 0); warp_changed = true; }
-
                 }
                 if (warp_changed && lane == 0) __stcg(cnt + 4 + rnd % 3, 1);
                 cluster_sync_all();
@@ -602,10 +566,10 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
             for (int base = gwarp * 32; base < n; base += n_gwarps * 32) {   // one list entry per lane
                 const int my = base + lane;
                 int p_l = 0, v_l = 255;
-                if (my < n) { p_l = __ldcg(list + my); v_l = __ldcg(q_new + p_l); }
+                if (my < n) { p_l = __ldcg(list + my); v_l = __ldcg(q2 + 2 * p_l); }
                 if (v_l != 255) {
                     const float f = (float)(v_l + dm.dmin);
-                    __stcg(q_old + p_l, (uint8_t)v_l);
+                    __stcg(q2 + 2 * p_l + 1, (uint8_t)v_l);
                     __stcg(d_old + p_l, f);
                     __stcg(d_new + p_l, f);
                     __stcg(lab + p_l, (uint8_t)0);
@@ -634,227 +598,19 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
     if (gtid == 0) __stcg(cnt + 2, rounds_total);
 }
 
-__global__ void __cluster_dims__(RV_CLUSTER, 1, 1) __launch_bounds__(RV_THREADS)
-k_region_voting_tiles(AdcParams P, const uchar4* __restrict__ arms, float* disp_old, float* disp_new,
-                      uint8_t* dq, uint8_t* label, int* pend, int* counters, int* tile_stamp, int* tile_eval) {
-    extern __shared__ __align__(16) unsigned char rv_smem[];
-    const AdcDims& dm = P.dm;
-    const int reach = max(P.L1, 0);
-    const int E = RV_T + 2 * reach, ES = E + 1;         // staged edge and padded row stride (words)
-    uchar4* tile = reinterpret_cast<uchar4*>(rv_smem);                                   // [E][ES] {new, old, left, right}
-    int* s_hist_base = reinterpret_cast<int*>(rv_smem + (size_t)E * ES * 4);             // [RV_WARPS][RV_MAXD]
-    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_hist_base + RV_WARPS * RV_MAXD);  // [RV_T*RV_T]
-    __shared__ int s_tot[RV_WARPS];
-    __shared__ int s_tile, s_count, s_local_changed;
-
-    const int pair = blockIdx.x / RV_CLUSTER;
-    const int crank = blockIdx.x % RV_CLUSTER;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int gwarp = crank * RV_WARPS + wid, n_gwarps = RV_CLUSTER * RV_WARPS;
-    const int gtid = crank * RV_THREADS + tid, n_gthreads = RV_CLUSTER * RV_THREADS;
-    const int W = dm.W, H = dm.H, D = dm.D;
-    const int ntx = (W + RV_T - 1) / RV_T, nty = (H + RV_T - 1) / RV_T, n_tiles = ntx * nty;
-    const uchar4* A = arms + (size_t)pair * dm.N;
-    float* d_old = disp_old + (size_t)pair * dm.N;
-    float* d_new = disp_new + (size_t)pair * dm.N;
-    uint8_t* q_new = dq + ((size_t)pair * 2 + 0) * dm.N;
-    uint8_t* q_old = dq + ((size_t)pair * 2 + 1) * dm.N;
-    uint8_t* lab = label + (size_t)pair * dm.N;
-    int* stamps = tile_stamp + (size_t)pair * n_tiles;
-    int* evals_ep = tile_eval + (size_t)pair * 2 * n_tiles;
-    int* cnt = counters + pair * ADC_CNT;  // 0,1 list sizes; 2 rounds; 3 evaluations; 4..6 change flags; 7..9 tile queues
-    int n_list[2] = {__ldcg(cnt + 10), __ldcg(cnt + 11)};   // active (fillable) lists, see launch_active_lists
-    int rounds_total = 0, evals = 0;
-    int* hist = s_hist_base + wid * RV_MAXD;
-    const int grp = lane >> 3, sub = lane & 7;
-
-    for (int i = gtid; i < n_tiles; i += n_gthreads) { __stcg(stamps + i, 0); __stcg(evals_ep + i, 0); __stcg(evals_ep + n_tiles + i, 0); }
-    if (gtid < 6) __stcg(cnt + 4 + gtid, 0);
-    int epoch = 1, rnd = 0;
-    cluster_sync_all();
-
-    auto stamp_around = [&](int x, int y, int self_tile) {   // all lanes of the warp call this
-        const int tx0 = max(0, (x - reach) / RV_T), tx1 = min(ntx - 1, (x + reach) / RV_T);
-        const int ty0 = max(0, (y - reach) / RV_T), ty1 = min(nty - 1, (y + reach) / RV_T);
-        const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
-        for (int i = lane; i < nt; i += 32) {
-            const int t = (ty0 + i / nx) * ntx + tx0 + i % nx;
-            if (t != self_tile) __stcg(stamps + t, epoch);
-        }
-    };
-
-    for (int it = 0; it < 5; it++) {
-        for (int k = 0; k < 2; k++) {
-            int* list = pend + ((size_t)pair * 2 + k) * dm.N;
-            const int n = n_list[k];
-            if (n == 0) continue;  // uniform across the cluster
-            bool any_fill = false;
-            while (true) {
-                if (gtid == 0) { __stcg(cnt + 4 + (rnd + 1) % 3, 0); __stcg(cnt + 7 + (rnd + 1) % 3, 0); }
-                bool cta_changed = false;
-                while (true) {
-                    // ---- next tile from the round's queue
-                    __syncthreads();
-                    if (tid == 0) s_tile = atomicAdd(cnt + 7 + rnd % 3, 1);
-                    __syncthreads();
-                    const int t = s_tile;
-                    if (t >= n_tiles) break;
-                    if (__ldcg(stamps + t) < __ldcg(evals_ep + k * n_tiles + t)) continue;   // nothing changed near it since
-                    const int ty0 = (t / ntx) * RV_T, tx0 = (t % ntx) * RV_T;
-                    // ---- pending pixels of class k inside the tile, raster order
-                    int base = 0;
-                    for (int c0 = 0; c0 < RV_T * RV_T; c0 += RV_THREADS) {
-                        const int li = c0 + tid, ly = li / RV_T, lx = li % RV_T;
-                        const int gy = ty0 + ly, gx = tx0 + lx;
-                        const bool f = gy < H && gx < W && __ldcg(lab + gy * W + gx) == k + 1;   // L2: other CTAs clear labels at commit
-                        const unsigned bm = __ballot_sync(0xffffffffu, f);
-                        if (lane == 0) s_tot[wid] = __popc(bm);
-                        __syncthreads();
-                        int off = base, tot = 0;
-                        for (int w2 = 0; w2 < RV_WARPS; w2++) { const int c = s_tot[w2]; if (w2 < wid) off += c; tot += c; }
-                        if (f) s_list[off + __popc(bm & ((1u << lane) - 1u))] = (unsigned short)li;
-                        base += tot;
-                        __syncthreads();
-                    }
-                    const int count = base;
-                    if (count == 0) { if (tid == 0) __stcg(evals_ep + k * n_tiles + t, epoch); continue; }
-                    // ---- stage state bytes and horizontal arms of the tile + halo
-                    for (int i = tid; i < E * E; i += RV_THREADS) {
-                        const int ry = i / E, rx = i - ry * E;
-                        const int gy = ty0 - reach + ry, gx = tx0 - reach + rx;
-                        uchar4 v = make_uchar4(255, 255, 0, 0);
-                        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                            const int g = gy * W + gx;
-                            const uchar4 a = __ldg(A + g);
-                            v = make_uchar4(__ldcg(q_new + g), __ldcg(q_old + g), a.x, a.y);
-                        }
-                        tile[ry * ES + rx] = v;
-                    }
-                    __syncthreads();
-                    // ---- local fixed point
-                    bool capped = false;
-                    for (int inner = 0; inner < RV_INNER; inner++) {
-                        if (tid == 0) s_local_changed = 0;
-                        __syncthreads();
-                        for (int idx = wid; idx < count; idx += RV_WARPS) {
-                            const int li = s_list[idx], ly = li / RV_T, lx = li % RV_T;
-                            const int gy = ty0 + ly, gx = tx0 + lx, p = gy * W + gx;
-                            evals++;
-                            for (int b = lane; b < D; b += 32) hist[b] = 0;
-                            __syncwarp();
-                            const uchar4 a = __ldg(A + p);
-                            const int cy = ly + reach, cx = lx + reach;
-                            for (int tt = -(int)a.z + grp; tt <= (int)a.w; tt += 4) {
-                                const uchar4* rowp = tile + (cy + tt) * ES + cx;
-                                const uchar4 c0 = rowp[0];
-                                for (int ss = -(int)c0.z + sub; ss <= (int)c0.w; ss += 8) {
-                                    const uchar4 c = rowp[ss];
-                                    const bool before = (tt < 0) || (tt == 0 && ss < 0);
-                                    const int dv = before ? c.x : c.y;
-                                    if (dv < 254) atomicAdd(&hist[dv], 1);
-                                }
-                            }
-                            __syncwarp();
-                            int peak = 0, best = 0x7fffffff, total = 0;
-                            for (int b = lane; b < D; b += 32) {
-                                const int h = hist[b];
-                                if (peak < h) { peak = h; best = b; }
-                                total += h;
-                            }
-                            const int gpeak = __reduce_max_sync(0xffffffffu, peak);
-                            const int gbest = __reduce_min_sync(0xffffffffu, peak == gpeak ? best : 0x7fffffff);
-                            total = __reduce_add_sync(0xffffffffu, total);
-                            int r = 255;
-                            if (gpeak > 0 && total > P.irv_ts &&
-                                __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th)
-                                r = gbest;
-                            uchar4* self = tile + cy * ES + cx;
-                            const bool changed = r != (int)self->x;
-                            __syncwarp();
-                            if (changed) {
-                                if (lane == 0) { self->x = (unsigned char)r; __stcg(q_new + p, (uint8_t)r); s_local_changed = 1; }
-                                stamp_around(gx, gy, t);
-                                cta_changed = true;
-                            }
-                        }
-                        __syncthreads();
-                        const int lc = s_local_changed;
-                        __syncthreads();
-                        if (!lc) break;
-                        if (inner == RV_INNER - 1) capped = true;
-                    }
-                    if (tid == 0) {
-                        __stcg(evals_ep + k * n_tiles + t, epoch);
-                        if (capped) __stcg(stamps + t, epoch);   // not yet locally consistent: look again next round
-                    }
-                }
-                if (cta_changed && lane == 0) __stcg(cnt + 4 + rnd % 3, 1);   // every warp that saw a change
-                cluster_sync_all();
-                const int ch = __ldcg(cnt + 4 + rnd % 3);
-                rounds_total++;
-                epoch++;
-                rnd++;
-                if (!ch) break;
-                any_fill = true;
-            }
-            if (!any_fill) continue;
-            // ---- commit: OLD <- NEW for filled pixels (float maps too), stamp, erase from the list
-            for (int idx = gwarp; idx < n; idx += n_gwarps) {
-                const int p = __ldcg(list + idx);
-                const int v = __ldcg(q_new + p);
-                if (v != 255) {
-                    if (lane == 0) {
-                        const float f = (float)(v + dm.dmin);
-                        __stcg(q_old + p, (uint8_t)v);
-                        __stcg(d_old + p, f);
-                        __stcg(d_new + p, f);
-                        __stcg(lab + p, (uint8_t)0);
-                    }
-                    const int y = p / W;
-                    stamp_around(p - y * W, y, -1);
-                }
-            }
-            epoch++;
-            cluster_sync_all();
-            if (crank == 0) {
-                const int kept = rv_compact_invalid(n, list, d_old, s_tot);
-                if (tid == 0) __stcg(cnt + 10 + k, kept);
-            }
-            cluster_sync_all();
-            n_list[k] = __ldcg(cnt + 10 + k);
-        }
-    }
-    evals = __reduce_add_sync(0xffffffffu, lane == 0 ? evals : 0);
-    if (lane == 0) atomicAdd(cnt + 3, evals);
-    if (gtid == 0) __stcg(cnt + 2, rounds_total);
-}
-
 void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
     // disp_l = committed state (OLD), disp_t = working copy (NEW); both hold the post-outlier map here
     const int reach = P.L1 > 0 ? P.L1 : 0;
-    static int mode = -1;   // development switch: 1 = byte state via L1 (default), 0 = shared-memory tiles,
-                            // 2 = float state via L2, 3 = float state via L1
+    static int mode = -1;   // development switch: 1 = byte-state kernel (default), 2 = float state via L2, 3 = float state via L1
     if (mode < 0) { const char* m = getenv("ADC_VOTE_MODE"); mode = m ? atoi(m) : 1; }
     dim3 egrid((P.dm.N + 255) / 256, w.S);
     if (mode == 1 && P.dm.D <= 254) {
         launch_active_lists(P, w, st, launches);
         k_vote_encode<<<egrid, 256, 0, st>>>(P.dm, w.disp_l, w.arms, w.vote_dq, w.vote_alr);
         k_region_voting_bytes<<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.vote_alr, w.disp_l, w.disp_t, w.vote_dq,
-                                                                      w.label, w.vlist, w.counters, w.tile_stamp, w.last_eval, w.vote_dirty);
+                                                                      w.label, w.vlist, w.counters, w.tile_stamp, w.last_eval);
         *launches += 2;
         adc_launch_build_lists(P, w, st, launches);   // outlier lists = every listed pixel that is still invalid
-    } else if (mode == 0 && P.dm.D <= 254 && reach <= RV_MAXREACH) {
-        const int E = RV_T + 2 * reach;
-        const size_t smem = (size_t)E * (E + 1) * 4 + (size_t)RV_WARPS * RV_MAXD * 4 + (size_t)RV_T * RV_T * 2;
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(k_region_voting_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            attr_done = true;
-        }
-        k_vote_encode<<<egrid, 256, 0, st>>>(P.dm, w.disp_l, w.arms, w.vote_dq, w.vote_alr);
-        k_region_voting_tiles<<<w.S * RV_CLUSTER, RV_THREADS, smem, st>>>(P, w.arms, w.disp_l, w.disp_t, w.vote_dq, w.label,
-                                                                         w.pend, w.counters, w.tile_stamp, w.last_eval);
-        *launches += 2;
     } else {
         if (mode != 3)
             k_region_voting_global<false><<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.disp_l, w.disp_t, w.label, w.pend,

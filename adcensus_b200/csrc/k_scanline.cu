@@ -166,7 +166,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-template <int K, int LPS>
+template <int K, int LPS, bool FULL>   // FULL: D == LPS*K, every lane's K values are real disparities (no padding logic)
 __global__ void __launch_bounds__(SO_WARPS * 32)
 k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
            const unsigned* __restrict__ rec, int sx, int sy) {
@@ -207,7 +207,7 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
 
     bool valid[K];
 #pragma unroll
-    for (int k = 0; k < K; k++) valid[k] = (gl * K + k) < D;
+    for (int k = 0; k < K; k++) valid[k] = FULL || (gl * K + k) < D;
 
     // start the pipeline, then handle the path head: L = C  (scanline_optimizer.cpp:99-100)
 #pragma unroll
@@ -283,8 +283,8 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
     cp_async_wait<0>();
 }
 
-template <int K, int LPS>
-static int launch_scanline_k(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
+template <int K, int LPS, bool FULL>
+static int launch_scanline_kf(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
                              cudaStream_t st) {
     constexpr int LPW = 32 / LPS;
     const int n_lines = sx ? P.dm.H : P.dm.W;
@@ -292,13 +292,20 @@ static int launch_scanline_k(const AdcParams& P, const AdcWave& w, const float* 
     const size_t smem = (size_t)SO_WARPS * LPW * SO_PF * slot_bytes;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_scanline<K, LPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_scanline<K, LPS, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_done = true;
     }
     const int lines_per_block = SO_WARPS * LPW;
     dim3 grid((n_lines + lines_per_block - 1) / lines_per_block, w.S);
-    k_scanline<K, LPS><<<grid, SO_WARPS * 32, smem, st>>>(P, src, dst, w.so_rec, sx, sy);
+    k_scanline<K, LPS, FULL><<<grid, SO_WARPS * 32, smem, st>>>(P, src, dst, w.so_rec, sx, sy);
     return 0;
+}
+
+template <int K, int LPS>
+static int launch_scanline_k(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
+                             cudaStream_t st) {
+    if (P.dm.D == K * LPS) return launch_scanline_kf<K, LPS, true>(P, w, src, dst, sx, sy, st);
+    return launch_scanline_kf<K, LPS, false>(P, w, src, dst, sx, sy, st);
 }
 
 void adc_launch_so_bitrows(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
