@@ -656,10 +656,10 @@ int adc_debug_run(adc_engine* e, const uint8_t* img_left, const uint8_t* img_rig
     return ADC_OK;
 }
 
-int adc_debug_counters(adc_engine* e, int32_t out[8]) {
+int adc_debug_counters(adc_engine* e, int32_t out[16]) {
     if (!e || !out) return fail(ADC_ERR_ARG, "adc_debug_counters: bad arguments");
     CK(cudaSetDevice(e->cfg.device));
-    CK(cudaMemcpy(out, e->lanes[0].w.counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, e->lanes[0].w.counters, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return ADC_OK;
 }
 

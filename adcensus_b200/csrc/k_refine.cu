@@ -434,6 +434,8 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
     int n_list[2] = {__ldcg(cnt + 10), __ldcg(cnt + 11)};   // active (fillable) lists, see launch_active_lists
     int rounds_total = 0, evals = 0;
     int* hist = s_hist[wid];
+    unsigned long long t_work = 0, t_bar = 0, t_commit = 0, t_compact = 0, t0 = 0;
+    auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
 
     for (int i = gtid; i < tw * th; i += n_gthreads) __stcg(tiles + i, 0);
     for (int k = 0; k < 2; k++) {
@@ -453,6 +455,7 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
             while (true) {
                 if (gtid == 0) __stcg(cnt + 4 + (rnd + 1) % 3, 0);
                 bool warp_changed = false;
+                t0 = now();
                 // 32 list entries per warp trip: every lane checks one pending pixel (is its tile stamped since
                 // its last evaluation?), then the warp evaluates the dirty ones one after the other
                 // (entries are dealt so that neighbouring list entries -- neighbouring pixels, which tend to be
@@ -483,7 +486,10 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                         // (three per lane at most) and handed out by shuffle; then the region is visited in trips of
                         // 4 rows x 16 columns, software-pipelined (the loads of trip j+1 are in flight while trip j is
                         // added to the histogram).  Trip count = ceil(rows/4) x ceil(longest row/16): small regions cost
-                        // few instructions.  One 16-bit load brings a pixel's NEW and OLD state.
+                        // few instructions.  One 16-bit load brings a pixel's NEW and OLD state; it goes through L1
+                        // (ld.ca): neighbouring pixels are evaluated on the same SM and share their regions, and every
+                        // cluster barrier ends in CCTL.IVALL (see the SASS), so no line outlives a round.  A line going
+                        // stale inside a round is harmless (asynchronous fixed point; the certifying round writes nothing).
                         const int top = (int)(tb & 255u), rows = top + (int)(tb >> 8) + 1;
                         const int rbase = (y - top) * W + x;
                         unsigned ar0, ar1 = 0, ar2 = 0;
@@ -517,8 +523,8 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                             const int mid = t < 0 ? 0x10000 : (t == 0 ? 0 : -0x10000);   // columns below `mid` read NEW
                             const unsigned short* rp = q2w + rbase + ri * W;
                             o0 = o1 = 255;
-                            if (s0 <= s_hi) { const unsigned w2 = __ldcg(rp + s0); o0 = s0 < mid ? (int)(w2 & 255u) : (int)(w2 >> 8); }
-                            if (s1 <= s_hi) { const unsigned w2 = __ldcg(rp + s1); o1 = s1 < mid ? (int)(w2 & 255u) : (int)(w2 >> 8); }
+                            if (s0 <= s_hi) { const unsigned w2 = __ldca(rp + s0); o0 = s0 < mid ? (int)(w2 & 255u) : (int)(w2 >> 8); }
+                            if (s1 <= s_hi) { const unsigned w2 = __ldca(rp + s1); o1 = s1 < mid ? (int)(w2 & 255u) : (int)(w2 >> 8); }
                             if (++tc == ncp) { tc = 0; ti++; }
                         };
                         int d0, d1;
@@ -554,7 +560,9 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                     }
                 }
                 if (warp_changed && lane == 0) __stcg(cnt + 4 + rnd % 3, 1);
+                { const unsigned long long t1 = now(); t_work += t1 - t0; t0 = t1; }
                 cluster_sync_all();
+                { const unsigned long long t1 = now(); t_bar += t1 - t0; t0 = t1; }
                 const int ch = __ldcg(cnt + 4 + rnd % 3);
                 rounds_total++;
                 epoch++;
@@ -563,6 +571,7 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
                 any_fill = true;
             }
             if (!any_fill) continue;
+            t0 = now();
             for (int base = gwarp * 32; base < n; base += n_gwarps * 32) {   // one list entry per lane
                 const int my = base + lane;
                 int p_l = 0, v_l = 255;
@@ -585,17 +594,23 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
             }
             epoch++;
             cluster_sync_all();
+            { const unsigned long long t1 = now(); t_commit += t1 - t0; t0 = t1; }
             if (crank == 0) {
                 const int kept = rv_compact_invalid(n, list, d_old, s_tot);
                 if (tid == 0) __stcg(cnt + 10 + k, kept);
             }
             cluster_sync_all();
+            { const unsigned long long t1 = now(); t_compact += t1 - t0; t0 = t1; }
             n_list[k] = __ldcg(cnt + 10 + k);
         }
     }
     evals = __reduce_add_sync(0xffffffffu, lane == 0 ? evals : 0);
     if (lane == 0) atomicAdd(cnt + 3, evals);
-    if (gtid == 0) __stcg(cnt + 2, rounds_total);
+    if (gtid == 0) {
+        __stcg(cnt + 2, rounds_total);
+        __stcg(cnt + 12, (int)(t_work / 1000)); __stcg(cnt + 13, (int)(t_bar / 1000));     // warp 0's view, microseconds
+        __stcg(cnt + 14, (int)(t_commit / 1000)); __stcg(cnt + 15, (int)(t_compact / 1000));
+    }
 }
 
 void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {

@@ -98,7 +98,7 @@ def load_library() -> ctypes.CDLL:
     L.adc_debug_run.argtypes = [vp, u8p, u8p, i32]
     L.adc_debug_get.argtypes = [vp, i32, vp, ctypes.c_size_t]
     L.adc_debug_get.restype = ctypes.c_size_t
-    L.adc_debug_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_int32 * 8)]
+    L.adc_debug_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_int32 * 16)]
     _lib = L
     return L
 
@@ -207,7 +207,7 @@ class Engine:
         _check(self._L.adc_debug_run(self._h, left.ctypes.data, right.ctypes.data, STAGE[last_stage]))
 
     def counters(self):
-        out = (ctypes.c_int32 * 8)()
+        out = (ctypes.c_int32 * 16)()
         _check(self._L.adc_debug_counters(self._h, ctypes.byref(out)))
         return list(out)
 

@@ -151,8 +151,9 @@ enum {
 };
 int adc_debug_run(adc_engine* e, const uint8_t* img_left, const uint8_t* img_right, int32_t last_stage);
 /* region-voting statistics of pair 0 of the last run: out[0],out[1] = remaining mismatch / occlusion
- * list sizes, out[2] = fixed-point rounds, out[3] = vote evaluations */
-int adc_debug_counters(adc_engine* e, int32_t out[8]);
+ * list sizes, out[2] = fixed-point rounds, out[3] = vote evaluations, out[12..15] = microseconds one warp spent
+ * evaluating / waiting at round barriers / committing / compacting lists */
+int adc_debug_counters(adc_engine* e, int32_t out[16]);
 /* returns the tap's size in bytes (also when dst is NULL or cap is too small), 0 on error */
 size_t adc_debug_get(adc_engine* e, int32_t tap, void* dst, size_t cap);
 

@@ -49,5 +49,6 @@ if os.environ.get("ADC_SWEEP_S"):
 eng = A.Engine(w, h, A.ADCensusOption())
 for _ in range(3):
     d = eng.match(left, right)
-print("voting counters [mism, occl, rounds, evals]:", eng.counters()[:4])
+c = eng.counters()
+print("voting counters [mism, occl, rounds, evals]:", c[:4], "warp0 us [work, barrier, commit, compact]:", c[12:16])
 print("single-pair stage ms (cost, aggr, so, wta, refine, out):", [round(x, 3) for x in eng.last_stage_ms()])
