@@ -463,7 +463,7 @@ int adc_create(int32_t width, int32_t height, const adc_option* opt, const adc_c
     // wave size: enough scanlines in flight for the warp-per-line scanline kernels (~6k lines = 40 warps/SM)
     int S = e->cfg.wave_pairs;
     if (S <= 0) S = std::min(32, std::max(2, (6144 + std::min(width, height) - 1) / std::min(width, height)));
-    int nl = e->cfg.lanes > 0 ? e->cfg.lanes : 3;
+    int nl = e->cfg.lanes > 0 ? e->cfg.lanes : 4;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "cudaMemGetInfo failed"));
     while (true) {
