@@ -406,9 +406,8 @@ __global__ void k_vote_encode(AdcDims dm, const float* __restrict__ disp, const 
 // moves 4x fewer bytes.  Mutable state is read at L2 (ld.cg) -- the CTAs of the cluster sit on
 // different SMs -- the constant arms through the read-only path.
 // ---------------------------------------------------------------------------------------------
-// 32 registers per thread (two 1024-thread CTAs' worth per SM): the kernel is latency-bound and leaves most issue
-// slots idle, so it must not hog the register file -- the other lanes' bandwidth kernels run beside it on the same SMs.
-__global__ void __cluster_dims__(RV_CLUSTER, 1, 1) __launch_bounds__(RV_THREADS, 2)
+// (capping this kernel at 32 registers so that other lanes' kernels fit beside it was measured: slower overall)
+__global__ void __cluster_dims__(RV_CLUSTER, 1, 1) __launch_bounds__(RV_THREADS)
 k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restrict__ alr_all,
                       float* disp_old, float* disp_new, uint8_t* dq, uint8_t* label, int* pend, int* counters,
                       int* tile_stamp, int* last_eval) {
