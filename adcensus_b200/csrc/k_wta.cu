@@ -124,6 +124,16 @@ k_wta_tile(AdcDims dm, int wpx, const float* __restrict__ vol, float* __restrict
     const int col_hi = x0 + wpx - 1 + max(0, dm.dmax - 1);
     const int ncols = col_hi - col_lo + 1;
     const float* rowv = vol + (size_t)pair * dm.vol_stride + (size_t)y * dm.W * dm.Dp;
+    {   // warm L2 with the core columns of the CTA that runs ~one wave of CTAs later in launch order
+        long long lin = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + 148 * 4;
+        if (lin < (long long)gridDim.x * gridDim.y * gridDim.z) {
+            const int bx2 = (int)(lin % gridDim.x); lin /= gridDim.x;
+            const int by2 = (int)(lin % gridDim.y); const int bz2 = (int)(lin / gridDim.y);
+            const float* r2 = vol + (size_t)bz2 * dm.vol_stride + ((size_t)by2 * dm.W + (size_t)bx2 * wpx) * dm.Dp;
+            const int lines = min(wpx, dm.W - bx2 * wpx) * dm.Dp / 32;      // 128-byte lines of the core tile
+            for (int i = threadIdx.x; i < lines; i += blockDim.x) asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + (size_t)i * 32));
+        }
+    }
     for (int i = threadIdx.x; i < ncols * Q; i += blockDim.x) {
         const int c = i / Q, q = i - c * Q;
         const int x = col_lo + c;
