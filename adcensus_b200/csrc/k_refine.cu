@@ -898,8 +898,9 @@ k_median_wavefront(AdcDims dm, const float* __restrict__ in, float* __restrict__
                 res[r] = median9(v);
             }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
-            // ring slot (x & 3) of row y holds column x-4, last read by row y+1 one step ago
-            __syncthreads();
+            // Publish the results of this step.  Row y writes ring slot (x & 3); during this same step row y+1
+            // (at column x-2) reads slots (x-3..x-1) & 3 of row y -- three slots that differ from x & 3 -- so the
+            // writes need no barrier of their own; one barrier per step makes them visible to the next step.
 #pragma unroll
             for (int r = 0; r < MED_ROWS; r++) {
                 if (!act[r]) continue;
