@@ -81,6 +81,11 @@ struct AdcWave {            // device pointers of one wave (S pairs)
     int2* vote_dirty;       // [S][N]     region voting: work list of the current round
     uchar2* vote_alr;       // [S][N]     region voting: horizontal arms only (left, right)
     uint8_t* vote_dq;       // [S][2][N]  region voting: rounded disparity index per pixel, NEW and OLD state
+    uchar2* vote_atbT;      // [S][W][H]  region voting: vertical arms (top, bottom), transposed (a column is contiguous)
+    int* vote_pslotT;       // [S][W][H]  region voting: histogram slot of a pending pixel, -1 otherwise (transposed)
+    uint8_t* vote_val;      // [S][N]     region voting: current vote per slot (255 = none)
+    uint8_t* vote_dirtyb;   // [S][N]     region voting: slot's histogram changed since its last derive
+    uint8_t* vote_dead;     // [S][N]     region voting: slot was filled and committed
     const float* lut_ad;    // [766]  (1 - exp(-(s/3)/lambda_ad)) + 1, host libm expf
     const float* lut_cen;   // [64]   exp(-h/lambda_census)
     const double* ray_sin; const double* ray_cos; // [16] host libm sin/cos of the accumulated angles
@@ -105,6 +110,9 @@ int adc_launch_wta(const AdcParams& P, const AdcWave& w, const float* vol, cudaS
 void adc_launch_outlier(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
 void adc_launch_build_lists(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
 void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
+// incremental-histogram voting (k_vote.cu); expects the active lists (w.vlist, counters 10/11) and the byte state
+// (w.vote_dq, w.vote_alr); uses w.volB as histogram storage.  false = not applicable, nothing launched
+bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
 // k = 0: mismatch list, k = 1: occlusion list; reads disp_l, writes disp_t
 void adc_launch_interp_list(const AdcParams& P, const AdcWave& w, int k, cudaStream_t st, unsigned long long* launches);
 void adc_launch_discontinuity(const AdcParams& P, const AdcWave& w, const float* vol, cudaStream_t st, unsigned long long* launches);

@@ -129,6 +129,11 @@ size_t carve_lane(void* base, const AdcDims& dm, int S, AdcWave* w) {
     t.vote_dq = c.take<uint8_t>((size_t)S * 2 * N);
     t.vote_alr = c.take<uchar2>((size_t)S * N);
     t.vote_dirty = c.take<int2>((size_t)S * N);
+    t.vote_atbT = c.take<uchar2>((size_t)S * N);
+    t.vote_pslotT = c.take<int>((size_t)S * N);
+    t.vote_val = c.take<uint8_t>((size_t)S * N);
+    t.vote_dirtyb = c.take<uint8_t>((size_t)S * N);
+    t.vote_dead = c.take<uint8_t>((size_t)S * N);
     t.wta_key = c.take<unsigned long long>((size_t)S * N);
     t.rowcnt = c.take<int>((size_t)S * 2 * dm.H);
     t.so_bitrows = c.take<unsigned>((size_t)S * adc_so_bitrow_bytes(dm) / 4);

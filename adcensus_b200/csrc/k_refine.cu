@@ -617,9 +617,26 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
 void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
     // disp_l = committed state (OLD), disp_t = working copy (NEW); both hold the post-outlier map here
     const int reach = P.L1 > 0 ? P.L1 : 0;
-    static int mode = -1;   // development switch: 1 = byte-state kernel (default), 2 = float state via L2, 3 = float state via L1
-    if (mode < 0) { const char* m = getenv("ADC_VOTE_MODE"); mode = m ? atoi(m) : 1; }
+    static int mode = -1;   // development switch: 4 = incremental histograms (k_vote.cu, default), 1 = byte-state pull kernel,
+                            // 2 = float state via L2, 3 = float state via L1
+    if (mode < 0) { const char* m = getenv("ADC_VOTE_MODE"); mode = m ? atoi(m) : 4; }
     dim3 egrid((P.dm.N + 255) / 256, w.S);
+    if (mode == 4 && P.dm.D <= 254) {
+        launch_active_lists(P, w, st, launches);
+        k_vote_encode<<<egrid, 256, 0, st>>>(P.dm, w.disp_l, w.arms, w.vote_dq, w.vote_alr);
+        ++*launches;
+        if (adc_launch_vote_push(P, w, st, launches)) {
+            adc_launch_build_lists(P, w, st, launches);   // outlier lists = every listed pixel that is still invalid
+            return;
+        }
+        mode = 1;   // not applicable for these parameters: the pull kernel below (lists and byte state are ready)
+        k_region_voting_bytes<<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.vote_alr, w.disp_l, w.disp_t, w.vote_dq,
+                                                                      w.label, w.vlist, w.counters, w.tile_stamp, w.last_eval);
+        ++*launches;
+        adc_launch_build_lists(P, w, st, launches);
+        mode = 4;
+        return;
+    }
     if (mode == 1 && P.dm.D <= 254) {
         launch_active_lists(P, w, st, launches);
         k_vote_encode<<<egrid, 256, 0, st>>>(P.dm, w.disp_l, w.arms, w.vote_dq, w.vote_alr);

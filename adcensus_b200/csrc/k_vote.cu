@@ -1,0 +1,312 @@
+// k_vote.cu -- iterative region voting (reference: multistep_refiner.cpp:153-227), incremental form.
+//
+// The reference runs 5 iterations x {mismatch list, occlusion list}; inside a sweep the pixels are
+// visited in raster order and a filled pixel is immediately visible to the later ones.  For a pending
+// pixel p the vote is a histogram over its cross region R(p) (vertical arm of p, then the horizontal arm
+// of every pixel on it) of the rounded disparities of the valid pixels, reading q's value "as of now" if
+// q precedes p in raster order and "as of the start of the sweep" otherwise.
+//
+// Exact parallel form used here.  Every pending pixel owns a histogram in memory that is kept equal to
+// what the reference's scan would count for it, and the sweep is the fixed point of
+//     derive: value(p) = vote(hist(p))                     for every p whose histogram changed
+//     push:   value(q) changed a -> b  =>  hist(p)[a]--, hist(p)[b]++   for every pending p of the swept
+//             list with q in R(p) and p after q in raster order
+// iterated until no value changes.  The sequential result is the unique fixed point of that map
+// (induction over raster order: the first pending pixel depends on nothing that moves, pixel p only on
+// earlier ones), so the iteration order is free; a round without changes certifies it.  When a sweep has
+// converged its fills are committed: they become visible to the pixels BEFORE them and to the other list
+// (one more push of "invalid -> b"), and the filled pixels leave the lists.  Histogram counts are
+// integers, so the order of the pushes is irrelevant; derive and push never overlap (CTA barrier between
+// them), so every derive sees a consistent histogram.
+//
+// Why: the pull form (re-scan R(p) whenever something near p changed) visits ~27 M pixels per Cone pair
+// behind a tile-granular "dirty" filter; the sequential reference 7.7 M.  Here the regions are scanned
+// ONCE (2.7 M visits, by a separate batch-wide kernel), and the iterative part is 12.7 k value changes,
+// each enumerating the pixels whose region contains it (the inverse region, ~270 candidate tests with the
+// transposed arm tables below) and touching ~40 histograms, plus 32 k 64-bin derives.  All of that fits
+// one CTA per stereo pair with nothing but CTA barriers between rounds.
+#include "adc_common.cuh"
+
+#define VP_THREADS 512
+#define VP_WARPS (VP_THREADS / 32)
+#define VI_WARPS 8
+#define VP_MAXD 256
+
+// ---- transposed per-pixel tables: vertical arms (top,bottom) as [x][y] so that a column is contiguous ----
+__global__ void __launch_bounds__(256)
+k_vote_transpose(AdcDims dm, const uchar4* __restrict__ arms, uchar2* __restrict__ atbT) {
+    __shared__ uchar2 tile[32][33];
+    const int pair = blockIdx.z;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const uchar4* A = arms + (size_t)pair * dm.N;
+    uchar2* T = atbT + (size_t)pair * dm.N;
+    for (int j = ty; j < 32; j += 8) {
+        const int x = x0 + tx, y = y0 + j;
+        if (x < dm.W && y < dm.H) { const uchar4 a = __ldg(A + y * dm.W + x); tile[j][tx] = make_uchar2(a.z, a.w); }
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int x = x0 + j, y = y0 + tx;
+        if (x < dm.W && y < dm.H) T[(size_t)x * dm.H + y] = tile[tx][j];
+    }
+}
+
+// ---- initial histograms: one warp per pending pixel (slot), the only full region scans of the stage ----
+// slot numbering: list 0 (mismatches) first, then list 1 (occlusions): slot = position in the active list
+// (+ n0 for list 1).  hist[slot] = D counters packed two per 32-bit word (a region holds < 65536 pixels:
+// adc_launch_vote_push checks (2*L1+1)^2).
+__global__ void __launch_bounds__(VI_WARPS * 32)
+k_vote_init(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restrict__ alr_all,
+            const uint8_t* __restrict__ dq, const int* __restrict__ vlist, const int* __restrict__ counters,
+            unsigned* __restrict__ hist_all, long long hist_stride, uint8_t* __restrict__ val_all,
+            uint8_t* __restrict__ dirty_all, uint8_t* __restrict__ dead_all, int* __restrict__ pslotT_all) {
+    __shared__ int s_hist[VI_WARPS][VP_MAXD];
+    const AdcDims& dm = P.dm;
+    const int pair = blockIdx.y;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int W = dm.W, H = dm.H, D = dm.D, HW = (D + 1) >> 1;
+    const int n0 = counters[pair * ADC_CNT + 10], n1 = counters[pair * ADC_CNT + 11];
+    const uchar4* A = arms + (size_t)pair * dm.N;
+    const uchar2* ALR = alr_all + (size_t)pair * dm.N;
+    const uint8_t* q2 = dq + (size_t)pair * 2 * dm.N;   // [2p] = rounded disparity index (255 = invalid, 254 = out of range)
+    unsigned* hist = hist_all + (size_t)pair * hist_stride;
+    int* hs = s_hist[wid];
+    const int half = lane >> 4, sub = lane & 15;
+    for (int s = blockIdx.x * VI_WARPS + wid; s < n0 + n1; s += gridDim.x * VI_WARPS) {
+        const int p = s < n0 ? vlist[((size_t)pair * 2 + 0) * dm.N + s] : vlist[((size_t)pair * 2 + 1) * dm.N + (s - n0)];
+        const int y = p / W, x = p - y * W;
+        for (int b = lane; b < D; b += 32) hs[b] = 0;
+        __syncwarp();
+        const uchar4 a = __ldg(A + p);
+        const int top = a.z, rows = top + (int)a.w + 1;
+        // two region rows per trip, one per half-warp; 16 columns per step
+        for (int r0 = 0; r0 < rows; r0 += 2) {
+            const int ri = r0 + half;
+            if (ri < rows) {
+                const int rowi = (y - top + ri) * W + x;
+                const uchar2 ar = __ldg(ALR + rowi);
+                for (int c = -(int)ar.x + sub; c <= (int)ar.y; c += 16) {
+                    const int v = q2[2 * (rowi + c)];
+                    if (v < D) atomicAdd(&hs[v], 1);
+                }
+            }
+        }
+        __syncwarp();
+        for (int w2 = lane; w2 < HW; w2 += 32) {
+            const unsigned c0 = (unsigned)hs[2 * w2], c1 = (2 * w2 + 1 < D) ? (unsigned)hs[2 * w2 + 1] : 0u;
+            hist[(size_t)s * HW + w2] = c0 | (c1 << 16);
+        }
+        if (lane == 0) {
+            val_all[(size_t)pair * dm.N + s] = 255;
+            dirty_all[(size_t)pair * dm.N + s] = 1;
+            dead_all[(size_t)pair * dm.N + s] = 0;
+            pslotT_all[(size_t)pair * dm.N + (size_t)x * H + y] = s;
+        }
+        __syncwarp();
+    }
+}
+
+// One CTA per stereo pair.  Mutable state (histograms, values, flags, slot table) is read and written at
+// L2 (ld.cg / st.cg / red), the immutable arm tables through the read-only path.
+__global__ void __launch_bounds__(VP_THREADS)
+k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __restrict__ atbT_all, int* pslotT_all,
+            unsigned* hist_all, long long hist_stride, uint8_t* val_all, uint8_t* dirty_all, uint8_t* dead_all,
+            const int* __restrict__ vlist, int* counters, int* work_all, int2* chg_all,
+            float* disp_old, float* disp_new, uint8_t* label) {
+    __shared__ int s_nwork, s_nchg;
+    const AdcDims& dm = P.dm;
+    const int pair = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int W = dm.W, H = dm.H, D = dm.D, HW = (D + 1) >> 1;
+    const int L1 = max(P.L1, 0);
+    const uchar2* ALR = alr_all + (size_t)pair * dm.N;
+    const uchar2* ATB = atbT_all + (size_t)pair * dm.N;
+    int* pslotT = pslotT_all + (size_t)pair * dm.N;
+    unsigned* hist = hist_all + (size_t)pair * hist_stride;
+    uint8_t* val = val_all + (size_t)pair * dm.N;
+    uint8_t* dirty = dirty_all + (size_t)pair * dm.N;
+    uint8_t* dead = dead_all + (size_t)pair * dm.N;
+    int* work = work_all + (size_t)pair * dm.N;
+    int2* chg = chg_all + (size_t)pair * dm.N;
+    float* d_old = disp_old + (size_t)pair * dm.N;
+    float* d_new = disp_new + (size_t)pair * dm.N;
+    uint8_t* lab = label + (size_t)pair * dm.N;
+    int* cnt = counters + pair * ADC_CNT;
+    const int n0 = __ldcg(cnt + 10), n1 = __ldcg(cnt + 11);
+    int rounds_total = 0, derives = 0, changes = 0;
+
+    // value change of pixel q (a -> b, 255 = invalid) -> histograms of the pending pixels whose region holds q.
+    //   phase 0 (inside the sweep of list k): pixels of list k that come after q in raster order
+    //   phase 1 (commit, a == 255):           pixels of list k before q, and every pixel of the other list
+    // Inverse region: p' = (px,py) has q = (qx,qy) in R(p') iff the horizontal arm of (px,qy) reaches qx and the
+    // vertical arm of (px,py) reaches qy.  Row scan over px (32 candidates per trip), then per hit column a scan over
+    // py on the transposed tables (contiguous), one candidate per lane.
+    auto push = [&](int q, int a, int b, int k, int phase) {
+        const int qy = q / W, qx = q - qy * W;
+        for (int c0 = 0; c0 <= 2 * L1; c0 += 32) {
+            const int px_l = qx - L1 + c0 + lane;
+            bool cover = false;
+            if (px_l >= 0 && px_l < W && c0 + lane <= 2 * L1) {
+                const uchar2 ar = __ldg(ALR + qy * W + px_l);     // (left, right) of (px, qy)
+                cover = px_l >= qx ? (px_l - qx <= (int)ar.x) : (qx - px_l <= (int)ar.y);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, cover);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int px = qx - L1 + c0 + src;
+                const uchar2* col = ATB + (size_t)px * H;
+                const int* ps = pslotT + (size_t)px * H;
+                for (int r0 = 0; r0 <= 2 * L1; r0 += 32) {
+                    const int py = qy - L1 + r0 + lane;
+                    if (py < 0 || py >= H || r0 + lane > 2 * L1) continue;
+                    const uchar2 tb = __ldg(col + py);            // (top, bottom) of (px, py)
+                    const bool cov = py >= qy ? (py - qy <= (int)tb.x) : (qy - py <= (int)tb.y);
+                    if (!cov) continue;
+                    const int s = __ldcg(ps + py);
+                    if (s < 0) continue;
+                    const int kk = s >= n0 ? 1 : 0;
+                    const bool after = py > qy || (py == qy && px > qx);
+                    bool go;
+                    if (phase == 0) go = kk == k && after;
+                    else            go = (kk != k || !after) && __ldcg(val + s) == 255;
+                    if (!go) continue;
+                    unsigned* h = hist + (size_t)s * HW;
+                    if (a < D) atomicSub(h + (a >> 1), 1u << ((a & 1) * 16));
+                    if (b < D) atomicAdd(h + (b >> 1), 1u << ((b & 1) * 16));
+                    __stcg(dirty + s, (uint8_t)1);
+                }
+            }
+        }
+    };
+
+    for (int it = 0; it < 5; it++) {
+        for (int k = 0; k < 2; k++) {
+            const int n = k == 0 ? n0 : n1, base = k == 0 ? 0 : n0;
+            if (n == 0) continue;
+            const int* list = vlist + ((size_t)pair * 2 + k) * dm.N;
+            bool any_change = false;
+            while (true) {
+                if (tid == 0) { s_nwork = 0; s_nchg = 0; }
+                __syncthreads();
+                // ---- collect the pixels of this list whose histogram changed since their last derive
+                for (int i0 = 0; i0 < n; i0 += VP_THREADS) {
+                    const int i = i0 + tid;
+                    const bool d = i < n && __ldcg(dirty + base + i) != 0;
+                    if (d) __stcg(dirty + base + i, (uint8_t)0);
+                    const unsigned m = __ballot_sync(0xffffffffu, d);
+                    int off = 0;
+                    if (lane == 0 && m) off = atomicAdd(&s_nwork, __popc(m));
+                    off = __shfl_sync(0xffffffffu, off, 0);
+                    if (d) work[off + __popc(m & ((1u << lane) - 1u))] = i;
+                }
+                __syncthreads();
+                const int nwork = s_nwork;
+                if (nwork == 0) break;
+                rounds_total++;
+                // ---- derive: vote of every such pixel from its histogram (multistep_refiner.cpp:199-214)
+                for (int t = wid; t < nwork; t += VP_WARPS) {
+                    const int i = __ldcg(work + t), s = base + i;
+                    const unsigned* h = hist + (size_t)s * HW;
+                    int peak = 0, best = 0x7fffffff, total = 0;
+                    for (int w2 = lane; w2 < HW; w2 += 32) {
+                        const unsigned v = __ldcg(h + w2);
+                        const int c0 = (int)(v & 0xffffu), c1 = (int)(v >> 16);
+                        if (peak < c0) { peak = c0; best = 2 * w2; }       // strict '<': the lowest disparity wins ties
+                        if (peak < c1) { peak = c1; best = 2 * w2 + 1; }
+                        total += c0 + c1;
+                    }
+                    const int gpeak = __reduce_max_sync(0xffffffffu, peak);
+                    const int gbest = __reduce_min_sync(0xffffffffu, peak == gpeak ? best : 0x7fffffff);
+                    total = __reduce_add_sync(0xffffffffu, total);
+                    int r = 255;
+                    if (gpeak > 0 && total > P.irv_ts &&
+                        __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th)
+                        r = gbest;
+                    if (lane == 0) {
+                        derives++;
+                        const int a = __ldcg(val + s);
+                        if (r != a) {
+                            __stcg(val + s, (uint8_t)r);
+                            const int c = atomicAdd(&s_nchg, 1);
+                            chg[c] = make_int2(__ldg(list + i), a | (r << 8));
+                        }
+                    }
+                }
+                __syncthreads();
+                const int nchg = s_nchg;
+                if (nchg == 0) break;
+                any_change = true;
+                changes += nchg;
+                // ---- push the changes into the histograms of the later pixels of this list
+                for (int t = wid; t < nchg; t += VP_WARPS) {
+                    const int2 c = chg[t];
+                    push(c.x, c.y & 255, (c.y >> 8) & 255, k, 0);
+                }
+                __syncthreads();
+            }
+            if (!any_change) continue;   // nothing moved in this sweep (uniform across the CTA)
+            // ---- commit: the pixels filled by this sweep become visible to everybody and leave the list
+            if (tid == 0) s_nchg = 0;
+            __syncthreads();
+            for (int i0 = 0; i0 < n; i0 += VP_THREADS) {
+                const int i = i0 + tid;
+                bool f = false;
+                int v = 255;
+                if (i < n && __ldcg(dead + base + i) == 0) { v = __ldcg(val + base + i); f = v != 255; }
+                const unsigned m = __ballot_sync(0xffffffffu, f);
+                int off = 0;
+                if (lane == 0 && m) off = atomicAdd(&s_nchg, __popc(m));
+                off = __shfl_sync(0xffffffffu, off, 0);
+                if (f) {
+                    const int p = __ldg(list + i);
+                    const float fv = (float)(v + dm.dmin);
+                    __stcg(dead + base + i, (uint8_t)1);
+                    d_old[p] = fv;
+                    d_new[p] = fv;
+                    lab[p] = 0;
+                    chg[off + __popc(m & ((1u << lane) - 1u))] = make_int2(p, 255 | (v << 8));
+                }
+            }
+            __syncthreads();
+            const int ncommit = s_nchg;
+            changes += ncommit;
+            for (int t = wid; t < ncommit; t += VP_WARPS) {
+                const int2 c = chg[t];
+                push(c.x, 255, (c.y >> 8) & 255, k, 1);
+            }
+            __syncthreads();
+            for (int t = tid; t < ncommit; t += VP_THREADS) {
+                const int p = chg[t].x, y = p / W, x = p - y * W;
+                __stcg(pslotT + (size_t)x * H + y, -1);
+            }
+            __syncthreads();
+        }
+    }
+    derives = __reduce_add_sync(0xffffffffu, lane == 0 ? derives : 0);
+    if (lane == 0) atomicAdd(cnt + 3, derives);
+    if (tid == 0) { __stcg(cnt + 2, rounds_total); __stcg(cnt + 12, changes); }
+}
+
+// returns false when the fast path does not apply (caller falls back to the pull kernels)
+bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
+    const AdcDims& dm = P.dm;
+    const int L1 = P.L1 > 0 ? P.L1 : 0;
+    if (dm.D > 254 || (2 * L1 + 1) * (2 * L1 + 1) > 65535) return false;
+    if ((long long)dm.N * ((dm.D + 1) / 2) > dm.vol_stride) return false;   // histograms live in the idle cost volume
+    cudaMemsetAsync(w.vote_pslotT, 0xff, (size_t)w.S * dm.N * sizeof(int), st);
+    dim3 tgrid((dm.W + 31) / 32, (dm.H + 31) / 32, w.S);
+    k_vote_transpose<<<tgrid, 256, 0, st>>>(dm, w.arms, w.vote_atbT);
+    unsigned* hist = reinterpret_cast<unsigned*>(w.volB);
+    int gx = (148 * 8 + w.S - 1) / w.S;
+    if (gx < 1) gx = 1;
+    dim3 igrid(gx, w.S);
+    k_vote_init<<<igrid, VI_WARPS * 32, 0, st>>>(P, w.arms, w.vote_alr, w.vote_dq, w.vlist, w.counters, hist, dm.vol_stride,
+                                                 w.vote_val, w.vote_dirtyb, w.vote_dead, w.vote_pslotT);
+    k_vote_push<<<w.S, VP_THREADS, 0, st>>>(P, w.vote_alr, w.vote_atbT, w.vote_pslotT, hist, dm.vol_stride, w.vote_val,
+                                           w.vote_dirtyb, w.vote_dead, w.vlist, w.counters, w.last_eval, w.vote_dirty,
+                                           w.disp_l, w.disp_t, w.label);
+    *launches += 3;
+    return true;
+}
