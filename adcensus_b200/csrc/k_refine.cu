@@ -692,26 +692,44 @@ k_interpolate(AdcParams P, int k, const uint8_t* __restrict__ bgr, const float* 
         float dval = ADC_LARGE_F;
         bool found = false;
         if (active) {
-            const uchar3 c0 = adc_load_bgr(left, p);
-            for (int m = 1; m < P.max_search; m++) {
-                long yy, xx;
-                if (ray_off) {   // integer offsets, verified on the host to equal the expression below for this image size
-                    const short2 o = __ldg(ray_off + ray * P.max_search + m);
-                    yy = y + o.y; xx = x + o.x;
-                } else {
-                    yy = lround(__dadd_rn((double)y, __dmul_rn((double)m, sa)));
-                    xx = lround(__dadd_rn((double)x, __dmul_rn((double)m, ca)));
+            // The walk stops at the first valid disparity, but nothing of step m+1 depends on step m except that
+            // stop: the loads of four consecutive steps go out together (one memory round trip per four steps
+            // instead of one per step), then the four are examined in order.
+            const int msteps = P.max_search;
+            for (int m0 = 1; m0 < msteps && !found; m0 += 4) {
+                int qq[4];
+                float dd[4];
+                bool out = false;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int m = m0 + j;
+                    qq[j] = -1;
+                    if (m < msteps && !out) {
+                        long yy, xx;
+                        if (ray_off) {   // integer offsets, verified on the host to equal the expression below for this image size
+                            const short2 o = __ldg(ray_off + ray * msteps + m);
+                            yy = y + o.y; xx = x + o.x;
+                        } else {
+                            yy = lround(__dadd_rn((double)y, __dmul_rn((double)m, sa)));
+                            xx = lround(__dadd_rn((double)x, __dmul_rn((double)m, ca)));
+                        }
+                        if (yy < 0 || yy >= dm.H || xx < 0 || xx >= dm.W) out = true;   // the ray ends at the image border
+                        else qq[j] = (int)yy * dm.W + (int)xx;
+                    }
                 }
-                if (yy < 0 || yy >= dm.H || xx < 0 || xx >= dm.W) break;
-                const int q = (int)yy * dm.W + (int)xx;
-                const float d = d_old[q];
-                if (d != ADC_INVALID_F) {
-                    const uchar3 c = adc_load_bgr(left, q);
-                    dist = abs((int)c0.x - (int)c.x) + abs((int)c0.y - (int)c.y) + abs((int)c0.z - (int)c.z);
-                    dval = d;
-                    found = true;
-                    break;
+#pragma unroll
+                for (int j = 0; j < 4; j++) dd[j] = qq[j] >= 0 ? d_old[qq[j]] : ADC_INVALID_F;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (!found && qq[j] >= 0 && dd[j] != ADC_INVALID_F) {
+                        const uchar3 c0 = adc_load_bgr(left, p);
+                        const uchar3 c = adc_load_bgr(left, qq[j]);
+                        dist = abs((int)c0.x - (int)c.x) + abs((int)c0.y - (int)c.y) + abs((int)c0.z - (int)c.z);
+                        dval = dd[j];
+                        found = true;
+                    }
                 }
+                if (out) break;
             }
         }
         // combine the 16 rays of this pixel (half-warp)

@@ -27,7 +27,7 @@
 // one CTA per stereo pair with nothing but CTA barriers between rounds.
 #include "adc_common.cuh"
 
-#define VP_THREADS 512
+#define VP_THREADS 1024
 #define VP_WARPS (VP_THREADS / 32)
 #define VI_WARPS 8
 #define VP_MAXD 256
@@ -59,8 +59,7 @@ k_vote_transpose(AdcDims dm, const uchar4* __restrict__ arms, uchar2* __restrict
 __global__ void __launch_bounds__(VI_WARPS * 32)
 k_vote_init(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restrict__ alr_all,
             const uint8_t* __restrict__ dq, const int* __restrict__ vlist, const int* __restrict__ counters,
-            unsigned* __restrict__ hist_all, long long hist_stride, uint8_t* __restrict__ val_all,
-            uint8_t* __restrict__ dirty_all, uint8_t* __restrict__ dead_all, int* __restrict__ pslotT_all) {
+            unsigned* __restrict__ hist_all, long long hist_stride, int* __restrict__ pslotT_all) {
     __shared__ int s_hist[VI_WARPS][VP_MAXD];
     const AdcDims& dm = P.dm;
     const int pair = blockIdx.y;
@@ -97,89 +96,153 @@ k_vote_init(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restri
             const unsigned c0 = (unsigned)hs[2 * w2], c1 = (2 * w2 + 1 < D) ? (unsigned)hs[2 * w2 + 1] : 0u;
             hist[(size_t)s * HW + w2] = c0 | (c1 << 16);
         }
-        if (lane == 0) {
-            val_all[(size_t)pair * dm.N + s] = 255;
-            dirty_all[(size_t)pair * dm.N + s] = 1;
-            dead_all[(size_t)pair * dm.N + s] = 0;
-            pslotT_all[(size_t)pair * dm.N + (size_t)x * H + y] = s;
-        }
+        if (lane == 0) pslotT_all[(size_t)pair * dm.N + (size_t)x * H + y] = s;
         __syncwarp();
     }
 }
 
-// One CTA per stereo pair.  Mutable state (histograms, values, flags, slot table) is read and written at
-// L2 (ld.cg / st.cg / red), the immutable arm tables through the read-only path.
+// One CTA per stereo pair.  Per-slot state (current vote, dirty / dead flags) lives in shared memory when the
+// lists fit (VP_SMEM_SLOTS slots; global memory otherwise -- one CTA = one SM, so plain accesses are coherent);
+// the histograms live in global memory and are read at L2 (ld.cg) because the pushes are L2 atomics; the arm
+// and slot tables are immutable during the kernel and go through the read-only path.
+// Everything that waits on memory is issued in batches of independent loads: a push first collects the
+// columns whose horizontal arm reaches the changed pixel, then tests the candidates of four columns x three
+// row groups at a time (12 loads in flight per lane, then up to 12 slot look-ups); a derive handles two
+// pixels per trip.  The first version walked the candidates one dependent L2 round trip after the other
+// and spent 17 us per change; the rounds themselves are cheap (CTA barriers).
+#define VP_SMEM_SLOTS 32768
+#define VP_FLAG_DIRTY 1
+#define VP_FLAG_DEAD 2
+
 __global__ void __launch_bounds__(VP_THREADS)
-k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __restrict__ atbT_all, int* pslotT_all,
-            unsigned* hist_all, long long hist_stride, uint8_t* val_all, uint8_t* dirty_all, uint8_t* dead_all,
-            const int* __restrict__ vlist, int* counters, int* work_all, int2* chg_all,
-            float* disp_old, float* disp_new, uint8_t* label) {
+k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __restrict__ atbT_all,
+            const int* __restrict__ pslotT_all, unsigned* hist_all, long long hist_stride, uint8_t* val_all,
+            uint8_t* flag_all, const int* __restrict__ vlist, int* counters, int* work_all, int2* chg_all,
+            float* disp_old, float* disp_new, uint8_t* label, int cols_cap) {
+    extern __shared__ __align__(16) unsigned char vp_smem[];
     __shared__ int s_nwork, s_nchg;
     const AdcDims& dm = P.dm;
     const int pair = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int W = dm.W, H = dm.H, D = dm.D, HW = (D + 1) >> 1;
-    const int L1 = max(P.L1, 0);
+    const int L1 = max(P.L1, 0), R = 2 * L1 + 1;
     const uchar2* ALR = alr_all + (size_t)pair * dm.N;
     const uchar2* ATB = atbT_all + (size_t)pair * dm.N;
-    int* pslotT = pslotT_all + (size_t)pair * dm.N;
+    const int* pslotT = pslotT_all + (size_t)pair * dm.N;
     unsigned* hist = hist_all + (size_t)pair * hist_stride;
-    uint8_t* val = val_all + (size_t)pair * dm.N;
-    uint8_t* dirty = dirty_all + (size_t)pair * dm.N;
-    uint8_t* dead = dead_all + (size_t)pair * dm.N;
     int* work = work_all + (size_t)pair * dm.N;
     int2* chg = chg_all + (size_t)pair * dm.N;
     float* d_old = disp_old + (size_t)pair * dm.N;
     float* d_new = disp_new + (size_t)pair * dm.N;
     uint8_t* lab = label + (size_t)pair * dm.N;
     int* cnt = counters + pair * ADC_CNT;
-    const int n0 = __ldcg(cnt + 10), n1 = __ldcg(cnt + 11);
+    const int n0 = __ldcg(cnt + 10), n1 = __ldcg(cnt + 11), ns = n0 + n1;
+    unsigned short* cols = reinterpret_cast<unsigned short*>(vp_smem) + (size_t)wid * cols_cap;   // per warp: hit columns of a push
+    uint8_t* val;    // [slot] current vote, 255 = none
+    uint8_t* flg;    // [slot] VP_FLAG_*
+    if (ns <= VP_SMEM_SLOTS) {
+        val = vp_smem + (size_t)VP_WARPS * cols_cap * 2;
+        flg = val + VP_SMEM_SLOTS;
+        for (int i = tid; i < ns; i += VP_THREADS) { val[i] = 255; flg[i] = VP_FLAG_DIRTY; }
+    } else {
+        val = val_all + (size_t)pair * dm.N;
+        flg = flag_all + (size_t)pair * dm.N;
+        for (int i = tid; i < ns; i += VP_THREADS) { val[i] = 255; flg[i] = VP_FLAG_DIRTY; }
+    }
+    __syncthreads();
     int rounds_total = 0, derives = 0, changes = 0;
 
     // value change of pixel q (a -> b, 255 = invalid) -> histograms of the pending pixels whose region holds q.
     //   phase 0 (inside the sweep of list k): pixels of list k that come after q in raster order
     //   phase 1 (commit, a == 255):           pixels of list k before q, and every pixel of the other list
     // Inverse region: p' = (px,py) has q = (qx,qy) in R(p') iff the horizontal arm of (px,qy) reaches qx and the
-    // vertical arm of (px,py) reaches qy.  Row scan over px (32 candidates per trip), then per hit column a scan over
-    // py on the transposed tables (contiguous), one candidate per lane.
+    // vertical arm of (px,py) reaches qy.
     auto push = [&](int q, int a, int b, int k, int phase) {
         const int qy = q / W, qx = q - qy * W;
-        for (int c0 = 0; c0 <= 2 * L1; c0 += 32) {
+        // ---- columns px whose pixel (px, qy) reaches qx horizontally
+        int ncols = 0;
+        for (int c0 = 0; c0 < R; c0 += 32) {
             const int px_l = qx - L1 + c0 + lane;
             bool cover = false;
-            if (px_l >= 0 && px_l < W && c0 + lane <= 2 * L1) {
+            if (px_l >= 0 && px_l < W && c0 + lane < R) {
                 const uchar2 ar = __ldg(ALR + qy * W + px_l);     // (left, right) of (px, qy)
                 cover = px_l >= qx ? (px_l - qx <= (int)ar.x) : (qx - px_l <= (int)ar.y);
             }
-            unsigned m = __ballot_sync(0xffffffffu, cover);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const int px = qx - L1 + c0 + src;
-                const uchar2* col = ATB + (size_t)px * H;
-                const int* ps = pslotT + (size_t)px * H;
-                for (int r0 = 0; r0 <= 2 * L1; r0 += 32) {
-                    const int py = qy - L1 + r0 + lane;
-                    if (py < 0 || py >= H || r0 + lane > 2 * L1) continue;
-                    const uchar2 tb = __ldg(col + py);            // (top, bottom) of (px, py)
-                    const bool cov = py >= qy ? (py - qy <= (int)tb.x) : (qy - py <= (int)tb.y);
-                    if (!cov) continue;
-                    const int s = __ldcg(ps + py);
-                    if (s < 0) continue;
-                    const int kk = s >= n0 ? 1 : 0;
-                    const bool after = py > qy || (py == qy && px > qx);
-                    bool go;
-                    if (phase == 0) go = kk == k && after;
-                    else            go = (kk != k || !after) && __ldcg(val + s) == 255;
-                    if (!go) continue;
-                    unsigned* h = hist + (size_t)s * HW;
-                    if (a < D) atomicSub(h + (a >> 1), 1u << ((a & 1) * 16));
-                    if (b < D) atomicAdd(h + (b >> 1), 1u << ((b & 1) * 16));
-                    __stcg(dirty + s, (uint8_t)1);
+            const unsigned m = __ballot_sync(0xffffffffu, cover);
+            if (cover) cols[ncols + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(c0 + lane);
+            ncols += __popc(m);
+        }
+        __syncwarp();
+        // ---- candidates (px, py), py in [qy - L1, qy + L1]: four columns x three row groups per trip
+        for (int c = 0; c < ncols; c += 4) {
+            int px[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) px[j] = c + j < ncols ? qx - L1 + (int)cols[c + j] : -1;
+            for (int r0 = 0; r0 < R; r0 += 96) {
+                int slot[4][3];
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    const int ro = r0 + 32 * t + lane, py = qy - L1 + ro;
+                    const bool rok = ro < R && py >= 0 && py < H;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        slot[j][t] = -1;
+                        if (rok && px[j] >= 0) {
+                            const uchar2 tb = __ldg(ATB + (size_t)px[j] * H + py);   // (top, bottom) of (px, py)
+                            const bool cov = py >= qy ? (py - qy <= (int)tb.x) : (qy - py <= (int)tb.y);
+                            if (cov) slot[j][t] = -2;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    const int py = qy - L1 + r0 + 32 * t + lane;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (slot[j][t] == -2) slot[j][t] = __ldg(pslotT + (size_t)px[j] * H + py);
+                }
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    const int py = qy - L1 + r0 + 32 * t + lane;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int s = slot[j][t];
+                        if (s < 0) continue;
+                        const int kk = s >= n0 ? 1 : 0;
+                        const bool after = py > qy || (py == qy && px[j] > qx);
+                        const int f = flg[s];
+                        if (f & VP_FLAG_DEAD) continue;
+                        bool go;
+                        if (phase == 0) go = kk == k && after;
+                        else            go = (kk != k || !after) && val[s] == 255;
+                        if (!go) continue;
+                        unsigned* h = hist + (size_t)s * HW;
+                        if (a < D) atomicSub(h + (a >> 1), 1u << ((a & 1) * 16));
+                        if (b < D) atomicAdd(h + (b >> 1), 1u << ((b & 1) * 16));
+                        if (!(f & VP_FLAG_DIRTY)) flg[s] = (uint8_t)VP_FLAG_DIRTY;   // (all writers write the same value)
+                    }
                 }
             }
         }
+        __syncwarp();
     };
+
+    auto vote = [&](const unsigned hv[], int nw) -> int {   // multistep_refiner.cpp:199-214 on the packed histogram words of this lane
+        int peak = 0, best = 0x7fffffff, total = 0;
+        for (int i = 0; i < nw; i++) {
+            const int w2 = lane + 32 * i;
+            const int c0 = (int)(hv[i] & 0xffffu), c1 = (int)(hv[i] >> 16);
+            if (peak < c0) { peak = c0; best = 2 * w2; }       // strict '<': the lowest disparity wins ties
+            if (peak < c1) { peak = c1; best = 2 * w2 + 1; }
+            total += c0 + c1;
+        }
+        const int gpeak = __reduce_max_sync(0xffffffffu, peak);
+        const int gbest = __reduce_min_sync(0xffffffffu, peak == gpeak ? best : 0x7fffffff);
+        total = __reduce_add_sync(0xffffffffu, total);
+        if (gpeak > 0 && total > P.irv_ts && __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th) return gbest;
+        return 255;
+    };
+    const int nhw = (HW + 31) / 32;   // histogram words per lane (<= 4 for D <= 254)
 
     for (int it = 0; it < 5; it++) {
         for (int k = 0; k < 2; k++) {
@@ -193,8 +256,8 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
                 // ---- collect the pixels of this list whose histogram changed since their last derive
                 for (int i0 = 0; i0 < n; i0 += VP_THREADS) {
                     const int i = i0 + tid;
-                    const bool d = i < n && __ldcg(dirty + base + i) != 0;
-                    if (d) __stcg(dirty + base + i, (uint8_t)0);
+                    const bool d = i < n && (flg[base + i] & VP_FLAG_DIRTY);
+                    if (d) flg[base + i] = 0;
                     const unsigned m = __ballot_sync(0xffffffffu, d);
                     int off = 0;
                     if (lane == 0 && m) off = atomicAdd(&s_nwork, __popc(m));
@@ -205,32 +268,31 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
                 const int nwork = s_nwork;
                 if (nwork == 0) break;
                 rounds_total++;
-                // ---- derive: vote of every such pixel from its histogram (multistep_refiner.cpp:199-214)
-                for (int t = wid; t < nwork; t += VP_WARPS) {
-                    const int i = __ldcg(work + t), s = base + i;
-                    const unsigned* h = hist + (size_t)s * HW;
-                    int peak = 0, best = 0x7fffffff, total = 0;
-                    for (int w2 = lane; w2 < HW; w2 += 32) {
-                        const unsigned v = __ldcg(h + w2);
-                        const int c0 = (int)(v & 0xffffu), c1 = (int)(v >> 16);
-                        if (peak < c0) { peak = c0; best = 2 * w2; }       // strict '<': the lowest disparity wins ties
-                        if (peak < c1) { peak = c1; best = 2 * w2 + 1; }
-                        total += c0 + c1;
+                // ---- derive: vote of every such pixel from its histogram, two pixels per trip
+                for (int t = 2 * wid; t < nwork; t += 2 * VP_WARPS) {
+                    const bool two = t + 1 < nwork;
+                    const int iA = work[t], iB = two ? work[t + 1] : iA;
+                    unsigned hA[4], hB[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int w2 = lane + 32 * j;
+                        hA[j] = (j < nhw && w2 < HW) ? __ldcg(hist + (size_t)(base + iA) * HW + w2) : 0u;
+                        hB[j] = (j < nhw && w2 < HW) ? __ldcg(hist + (size_t)(base + iB) * HW + w2) : 0u;
                     }
-                    const int gpeak = __reduce_max_sync(0xffffffffu, peak);
-                    const int gbest = __reduce_min_sync(0xffffffffu, peak == gpeak ? best : 0x7fffffff);
-                    total = __reduce_add_sync(0xffffffffu, total);
-                    int r = 255;
-                    if (gpeak > 0 && total > P.irv_ts &&
-                        __fdiv_rn(__fmul_rn((float)gpeak, 1.0f), (float)total) > P.irv_th)
-                        r = gbest;
+                    const int rA = vote(hA, nhw), rB = vote(hB, nhw);
                     if (lane == 0) {
-                        derives++;
-                        const int a = __ldcg(val + s);
-                        if (r != a) {
-                            __stcg(val + s, (uint8_t)r);
-                            const int c = atomicAdd(&s_nchg, 1);
-                            chg[c] = make_int2(__ldg(list + i), a | (r << 8));
+                        derives += two ? 2 : 1;
+                        const int aA = val[base + iA];
+                        if (rA != aA) {
+                            val[base + iA] = (uint8_t)rA;
+                            chg[atomicAdd(&s_nchg, 1)] = make_int2(__ldg(list + iA), aA | (rA << 8));
+                        }
+                        if (two) {
+                            const int aB = val[base + iB];
+                            if (rB != aB) {
+                                val[base + iB] = (uint8_t)rB;
+                                chg[atomicAdd(&s_nchg, 1)] = make_int2(__ldg(list + iB), aB | (rB << 8));
+                            }
                         }
                     }
                 }
@@ -248,13 +310,14 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
             }
             if (!any_change) continue;   // nothing moved in this sweep (uniform across the CTA)
             // ---- commit: the pixels filled by this sweep become visible to everybody and leave the list
+            __syncthreads();
             if (tid == 0) s_nchg = 0;
             __syncthreads();
             for (int i0 = 0; i0 < n; i0 += VP_THREADS) {
                 const int i = i0 + tid;
                 bool f = false;
                 int v = 255;
-                if (i < n && __ldcg(dead + base + i) == 0) { v = __ldcg(val + base + i); f = v != 255; }
+                if (i < n && !(flg[base + i] & VP_FLAG_DEAD)) { v = val[base + i]; f = v != 255; }
                 const unsigned m = __ballot_sync(0xffffffffu, f);
                 int off = 0;
                 if (lane == 0 && m) off = atomicAdd(&s_nchg, __popc(m));
@@ -262,25 +325,22 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
                 if (f) {
                     const int p = __ldg(list + i);
                     const float fv = (float)(v + dm.dmin);
-                    __stcg(dead + base + i, (uint8_t)1);
                     d_old[p] = fv;
                     d_new[p] = fv;
                     lab[p] = 0;
-                    chg[off + __popc(m & ((1u << lane) - 1u))] = make_int2(p, 255 | (v << 8));
+                    chg[off + __popc(m & ((1u << lane) - 1u))] = make_int2(p, base + i);
                 }
             }
             __syncthreads();
             const int ncommit = s_nchg;
             changes += ncommit;
+            // (the filled pixels still count as pending here -- val != 255 keeps them out of the targets)
             for (int t = wid; t < ncommit; t += VP_WARPS) {
                 const int2 c = chg[t];
-                push(c.x, 255, (c.y >> 8) & 255, k, 1);
+                push(c.x, 255, (int)val[c.y], k, 1);
             }
             __syncthreads();
-            for (int t = tid; t < ncommit; t += VP_THREADS) {
-                const int p = chg[t].x, y = p / W, x = p - y * W;
-                __stcg(pslotT + (size_t)x * H + y, -1);
-            }
+            for (int t = tid; t < ncommit; t += VP_THREADS) flg[chg[t].y] = (uint8_t)VP_FLAG_DEAD;
             __syncthreads();
         }
     }
@@ -303,10 +363,17 @@ bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st,
     if (gx < 1) gx = 1;
     dim3 igrid(gx, w.S);
     k_vote_init<<<igrid, VI_WARPS * 32, 0, st>>>(P, w.arms, w.vote_alr, w.vote_dq, w.vlist, w.counters, hist, dm.vol_stride,
-                                                 w.vote_val, w.vote_dirtyb, w.vote_dead, w.vote_pslotT);
-    k_vote_push<<<w.S, VP_THREADS, 0, st>>>(P, w.vote_alr, w.vote_atbT, w.vote_pslotT, hist, dm.vol_stride, w.vote_val,
-                                           w.vote_dirtyb, w.vote_dead, w.vlist, w.counters, w.last_eval, w.vote_dirty,
-                                           w.disp_l, w.disp_t, w.label);
+                                                 w.vote_pslotT);
+    const int cols_cap = (2 * L1 + 1 + 7) / 8 * 8;
+    const size_t smem = (size_t)VP_WARPS * cols_cap * 2 + 2 * (size_t)VP_SMEM_SLOTS;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_vote_push, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done = true;
+    }
+    k_vote_push<<<w.S, VP_THREADS, smem, st>>>(P, w.vote_alr, w.vote_atbT, w.vote_pslotT, hist, dm.vol_stride, w.vote_val,
+                                              w.vote_dirtyb, w.vlist, w.counters, w.last_eval, w.vote_dirty,
+                                              w.disp_l, w.disp_t, w.label, cols_cap);
     *launches += 3;
     return true;
 }
