@@ -85,7 +85,10 @@ struct AdcWave {            // device pointers of one wave (S pairs)
     int* vote_pslotT;       // [S][W][H]  region voting: histogram slot of a pending pixel, -1 otherwise (transposed)
     uint8_t* vote_val;      // [S][N]     region voting: current vote per slot (255 = none)
     uint8_t* vote_dirtyb;   // [S][N]     region voting: slot's histogram changed since its last derive
-    uint8_t* vote_dead;     // [S][N]     region voting: slot was filled and committed
+    uint8_t* vote_dead;     // [S][N]     (unused)
+    int* vote_state;        // [S][N]     region voting: disparity index of a valid pixel, -1 invalid, -(slot+2) pending
+    int* vote_deg;          // [S][N]     region voting: adjacency list lengths / fill cursors per slot
+    int* vote_off;          // [S][N+1]   region voting: adjacency list offsets (CSR by target slot)
     const float* lut_ad;    // [766]  (1 - exp(-(s/3)/lambda_ad)) + 1, host libm expf
     const float* lut_cen;   // [64]   exp(-h/lambda_census)
     const double* ray_sin; const double* ray_cos; // [16] host libm sin/cos of the accumulated angles

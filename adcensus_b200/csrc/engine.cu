@@ -134,6 +134,9 @@ size_t carve_lane(void* base, const AdcDims& dm, int S, AdcWave* w) {
     t.vote_val = c.take<uint8_t>((size_t)S * N);
     t.vote_dirtyb = c.take<uint8_t>((size_t)S * N);
     t.vote_dead = c.take<uint8_t>((size_t)S * N);
+    t.vote_state = c.take<int>((size_t)S * N);
+    t.vote_deg = c.take<int>((size_t)S * N);
+    t.vote_off = c.take<int>((size_t)S * (N + 1));
     t.wta_key = c.take<unsigned long long>((size_t)S * N);
     t.rowcnt = c.take<int>((size_t)S * 2 * dm.H);
     t.so_bitrows = c.take<unsigned>((size_t)S * adc_so_bitrow_bytes(dm) / 4);

@@ -382,7 +382,7 @@ k_region_voting_global(AdcParams P, const uchar4* __restrict__ arms, float* disp
 // state is one byte per pixel (0..253 = index, 254 = valid but outside [0,D), 255 = invalid).
 // ---------------------------------------------------------------------------------------------
 __global__ void k_vote_encode(AdcDims dm, const float* __restrict__ disp, const uchar4* __restrict__ arms,
-                              uint8_t* __restrict__ dq, uchar2* __restrict__ alr) {   // dq: [2i] = NEW, [2i+1] = OLD
+                              uint8_t* __restrict__ dq, uchar2* __restrict__ alr, int* __restrict__ vstate) {   // dq: [2i] = NEW, [2i+1] = OLD
     const int pair = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dm.N) return;
@@ -393,6 +393,7 @@ __global__ void k_vote_encode(AdcDims dm, const float* __restrict__ disp, const 
         v = (di >= 0 && di < dm.D && di < 254) ? (uint8_t)di : (uint8_t)254;
     }
     reinterpret_cast<uchar2*>(dq + (size_t)pair * 2 * dm.N)[i] = make_uchar2(v, v);
+    if (vstate) vstate[(size_t)pair * dm.N + i] = v == 255 ? -1 : (int)v;   // k_vote.cu: index of a valid pixel, -1 = invalid
     const uchar4 a = arms[(size_t)pair * dm.N + i];
     alr[(size_t)pair * dm.N + i] = make_uchar2(a.x, a.y);   // horizontal arms, 2 bytes per pixel
 }
@@ -623,7 +624,7 @@ void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, un
     dim3 egrid((P.dm.N + 255) / 256, w.S);
     if (mode == 4 && P.dm.D <= 254) {
         launch_active_lists(P, w, st, launches);
-        k_vote_encode<<<egrid, 256, 0, st>>>(P.dm, w.disp_l, w.arms, w.vote_dq, w.vote_alr);
+        k_vote_encode<<<egrid, 256, 0, st>>>(P.dm, w.disp_l, w.arms, w.vote_dq, w.vote_alr, w.vote_state);
         ++*launches;
         if (adc_launch_vote_push(P, w, st, launches)) {
             adc_launch_build_lists(P, w, st, launches);   // outlier lists = every listed pixel that is still invalid
@@ -639,7 +640,7 @@ void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, un
     }
     if (mode == 1 && P.dm.D <= 254) {
         launch_active_lists(P, w, st, launches);
-        k_vote_encode<<<egrid, 256, 0, st>>>(P.dm, w.disp_l, w.arms, w.vote_dq, w.vote_alr);
+        k_vote_encode<<<egrid, 256, 0, st>>>(P.dm, w.disp_l, w.arms, w.vote_dq, w.vote_alr, nullptr);
         k_region_voting_bytes<<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.vote_alr, w.disp_l, w.disp_t, w.vote_dq,
                                                                       w.label, w.vlist, w.counters, w.tile_stamp, w.last_eval);
         *launches += 2;
@@ -692,44 +693,26 @@ k_interpolate(AdcParams P, int k, const uint8_t* __restrict__ bgr, const float* 
         float dval = ADC_LARGE_F;
         bool found = false;
         if (active) {
-            // The walk stops at the first valid disparity, but nothing of step m+1 depends on step m except that
-            // stop: the loads of four consecutive steps go out together (one memory round trip per four steps
-            // instead of one per step), then the four are examined in order.
-            const int msteps = P.max_search;
-            for (int m0 = 1; m0 < msteps && !found; m0 += 4) {
-                int qq[4];
-                float dd[4];
-                bool out = false;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int m = m0 + j;
-                    qq[j] = -1;
-                    if (m < msteps && !out) {
-                        long yy, xx;
-                        if (ray_off) {   // integer offsets, verified on the host to equal the expression below for this image size
-                            const short2 o = __ldg(ray_off + ray * msteps + m);
-                            yy = y + o.y; xx = x + o.x;
-                        } else {
-                            yy = lround(__dadd_rn((double)y, __dmul_rn((double)m, sa)));
-                            xx = lround(__dadd_rn((double)x, __dmul_rn((double)m, ca)));
-                        }
-                        if (yy < 0 || yy >= dm.H || xx < 0 || xx >= dm.W) out = true;   // the ray ends at the image border
-                        else qq[j] = (int)yy * dm.W + (int)xx;
-                    }
+            const uchar3 c0 = adc_load_bgr(left, p);
+            for (int m = 1; m < P.max_search; m++) {
+                long yy, xx;
+                if (ray_off) {   // integer offsets, verified on the host to equal the expression below for this image size
+                    const short2 o = __ldg(ray_off + ray * P.max_search + m);
+                    yy = y + o.y; xx = x + o.x;
+                } else {
+                    yy = lround(__dadd_rn((double)y, __dmul_rn((double)m, sa)));
+                    xx = lround(__dadd_rn((double)x, __dmul_rn((double)m, ca)));
                 }
-#pragma unroll
-                for (int j = 0; j < 4; j++) dd[j] = qq[j] >= 0 ? d_old[qq[j]] : ADC_INVALID_F;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (!found && qq[j] >= 0 && dd[j] != ADC_INVALID_F) {
-                        const uchar3 c0 = adc_load_bgr(left, p);
-                        const uchar3 c = adc_load_bgr(left, qq[j]);
-                        dist = abs((int)c0.x - (int)c.x) + abs((int)c0.y - (int)c.y) + abs((int)c0.z - (int)c.z);
-                        dval = dd[j];
-                        found = true;
-                    }
+                if (yy < 0 || yy >= dm.H || xx < 0 || xx >= dm.W) break;
+                const int q = (int)yy * dm.W + (int)xx;
+                const float d = d_old[q];
+                if (d != ADC_INVALID_F) {
+                    const uchar3 c = adc_load_bgr(left, q);
+                    dist = abs((int)c0.x - (int)c.x) + abs((int)c0.y - (int)c.y) + abs((int)c0.z - (int)c.z);
+                    dval = d;
+                    found = true;
+                    break;
                 }
-                if (out) break;
             }
         }
         // combine the 16 rays of this pixel (half-warp)
@@ -754,8 +737,105 @@ k_interpolate(AdcParams P, int k, const uint8_t* __restrict__ bgr, const float* 
     }
 }
 
+// Fast path of the same step, used when the integer ray table is available (it is whenever it was verified exact
+// for this image size, see engine.cu).  The generic kernel spends ~15 instructions per ray step on coordinates,
+// four bounds tests and a float load; here the walk runs on a padded byte map (0 = invalid pixel: keep going,
+// 1 = valid: candidate found, 2 = outside the image: the ray ends) with the ray table in shared memory as linear
+// offsets into that map: one shared load, one add, one byte load and a test per step.
+__global__ void __launch_bounds__(256)
+k_interp_map(AdcDims dm, int B, const float* __restrict__ disp, uint8_t* __restrict__ imap) {
+    const int Wp = dm.W + 2 * B, Hp = dm.H + 2 * B;
+    const int pair = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Wp * Hp) return;
+    const int yp = i / Wp, xp = i - yp * Wp;
+    const int y = yp - B, x = xp - B;
+    uint8_t v = 2;
+    if (y >= 0 && y < dm.H && x >= 0 && x < dm.W) v = disp[(size_t)pair * dm.N + y * dm.W + x] != ADC_INVALID_F ? 1 : 0;
+    imap[(size_t)pair * Wp * Hp + i] = v;
+}
+
+__global__ void __launch_bounds__(256)
+k_interpolate_fast(AdcParams P, int k, const unsigned* __restrict__ bgrx, const float* __restrict__ disp_old,
+                   float* __restrict__ disp_new, const int* __restrict__ pend, const int* __restrict__ counters,
+                   const short2* __restrict__ ray_off, const uint8_t* __restrict__ imap_all) {
+    extern __shared__ int ip_off[];   // [16][max_search]: dy * Wp + dx
+    const AdcDims& dm = P.dm;
+    const int L = P.max_search, B = L - 1, Wp = dm.W + 2 * B, Hp = dm.H + 2 * B;
+    for (int i = threadIdx.x; i < 16 * L; i += blockDim.x) { const short2 o = ray_off[i]; ip_off[i] = (int)o.y * Wp + (int)o.x; }
+    __syncthreads();
+    const int pair = blockIdx.y;
+    const int n = counters[pair * ADC_CNT + k];
+    const int* list = pend + ((size_t)pair * 2 + k) * dm.N;
+    const unsigned* left = bgrx + (size_t)pair * 2 * dm.N;   // packed B | G<<8 | R<<16
+    const float* d_old = disp_old + (size_t)pair * dm.N;
+    float* d_new = disp_new + (size_t)pair * dm.N;
+    const uint8_t* imap = imap_all + (size_t)pair * Wp * Hp;
+    const int ray = threadIdx.x & 15;
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int n_slots = (gridDim.x * blockDim.x) >> 4;
+    const unsigned half_mask = 0xffffu << (threadIdx.x & 16);
+    const int* myoff = ip_off + ray * L;
+    for (int base = 0; base < n; base += n_slots) {   // uniform trip count for the whole warp
+        const int idx = base + slot;
+        const bool active = idx < n;
+        int p = 0;
+        int dist = 0x7fffffff;
+        float dval = ADC_LARGE_F;
+        bool found = false;
+        if (active) {
+            p = list[idx];
+            const int y = p / dm.W, x = p - y * dm.W;
+            const uint8_t* c0p = imap + (y + B) * Wp + (x + B);
+            int m = 1, hit = 2;
+            for (; m < L; m++) {
+                hit = c0p[myoff[m]];
+                if (hit) break;
+            }
+            if (m < L && hit == 1) {
+                const short2 o = __ldg(ray_off + ray * L + m);
+                const int q = (y + o.y) * dm.W + (x + o.x);
+                const unsigned a = __ldg(left + p), b = __ldg(left + q);
+                const unsigned ad = __vabsdiffu4(a, b);
+                dist = (int)(ad & 255u) + (int)((ad >> 8) & 255u) + (int)((ad >> 16) & 255u);
+                dval = d_old[q];
+                found = true;
+            }
+        }
+        // combine the 16 rays of this pixel (half-warp) -- as in k_interpolate
+        const unsigned any = __ballot_sync(0xffffffffu, found) & half_mask;
+        float result = 0.0f;
+        if (k == 0) {
+            int key = (found && dist < 9999) ? ((dist << 4) | ray) : 0x7fffffff;
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+            const int win = key & 15;
+            const float dw = __shfl_sync(0xffffffffu, dval, (threadIdx.x & 16) | win);
+            if (key != 0x7fffffff) result = dw;
+        } else {
+            float mv = found ? dval : ADC_LARGE_F;
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) mv = fminf(mv, __shfl_xor_sync(0xffffffffu, mv, o));
+            result = mv;
+        }
+        if (any == 0) result = 0.0f;
+        if (active && ray == 0) d_new[p] = result;
+    }
+}
+
 void adc_launch_interp_list(const AdcParams& P, const AdcWave& w, int k, cudaStream_t st, unsigned long long* launches) {
     dim3 grid(592, w.S);
+    const int L = P.max_search, B = L - 1;
+    const size_t map_bytes = (size_t)(P.dm.W + 2 * B) * (P.dm.H + 2 * B);
+    if (w.ray_off && L >= 2 && map_bytes <= (size_t)P.dm.N * 8 && (size_t)16 * L * sizeof(int) <= 48 * 1024) {
+        uint8_t* imap = reinterpret_cast<uint8_t*>(w.vote_dirty);   // [S][N] int2 scratch of the voting step, idle by now
+        dim3 mgrid((unsigned)((map_bytes + 255) / 256), w.S);
+        k_interp_map<<<mgrid, 256, 0, st>>>(P.dm, B, w.disp_l, imap);
+        k_interpolate_fast<<<grid, 256, (size_t)16 * L * sizeof(int), st>>>(P, k, w.bgrx, w.disp_l, w.disp_t, w.pend, w.counters,
+                                                                            w.ray_off, imap);
+        *launches += 2;
+        return;
+    }
     k_interpolate<<<grid, 256, 0, st>>>(P, k, w.bgr, w.disp_l, w.disp_t, w.pend, w.counters, w.ray_sin, w.ray_cos, w.ray_off);
     ++*launches;
 }

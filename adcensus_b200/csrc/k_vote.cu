@@ -20,19 +20,26 @@
 // them), so every derive sees a consistent histogram.
 //
 // Why: the pull form (re-scan R(p) whenever something near p changed) visits ~27 M pixels per Cone pair
-// behind a tile-granular "dirty" filter; the sequential reference 7.7 M.  Here the regions are scanned
-// ONCE (2.7 M visits, by a separate batch-wide kernel), and the iterative part is 12.7 k value changes,
-// each enumerating the pixels whose region contains it (the inverse region, ~270 candidate tests with the
-// transposed arm tables below) and touching ~40 histograms, plus 32 k 64-bin derives.  All of that fits
-// one CTA per stereo pair with nothing but CTA barriers between rounds.
+// behind a tile-granular "dirty" filter; the sequential reference 7.7 M.  Here the regions are scanned by
+// two batch-wide kernels (2.7 M visits each): the first builds the histograms and counts, for every pending
+// pixel t, how many regions contain it; the second writes those regions' owners into t's adjacency list
+// (CSR by target).  Only pending pixels ever change, so a value change of t is then: walk t's list (~40
+// entries, coalesced) and touch those histograms.  The iterative part -- 12.7 k value changes, 32 k 64-bin
+// derives, ~50 rounds -- fits one CTA per stereo pair with nothing but CTA barriers between rounds.
+// If the adjacency lists do not fit the idle cost volume they live in (pathological inputs: huge regions
+// that are almost entirely invalid), the pair falls back to enumerating the inverse region of every change
+// on the fly from transposed arm tables (push_enum below).
 #include "adc_common.cuh"
+#include <stdlib.h>
 
 #define VP_THREADS 1024
 #define VP_WARPS (VP_THREADS / 32)
 #define VI_WARPS 8
 #define VP_MAXD 256
+// counters (ADC_CNT ints per pair): 10/11 = active list sizes, 12 = changes, 13 = 1 when the adjacency lists are
+// in use, 14 = total adjacency entries
 
-// ---- transposed per-pixel tables: vertical arms (top,bottom) as [x][y] so that a column is contiguous ----
+// ---- transposed per-pixel tables for the fallback: vertical arms (top,bottom) as [x][y] ----
 __global__ void __launch_bounds__(256)
 k_vote_transpose(AdcDims dm, const uchar4* __restrict__ arms, uchar2* __restrict__ atbT) {
     __shared__ uchar2 tile[32][33];
@@ -52,72 +59,144 @@ k_vote_transpose(AdcDims dm, const uchar4* __restrict__ arms, uchar2* __restrict
     }
 }
 
-// ---- initial histograms: one warp per pending pixel (slot), the only full region scans of the stage ----
-// slot numbering: list 0 (mismatches) first, then list 1 (occlusions): slot = position in the active list
-// (+ n0 for list 1).  hist[slot] = D counters packed two per 32-bit word (a region holds < 65536 pixels:
-// adc_launch_vote_push checks (2*L1+1)^2).
+// ---- slots.  slot = position in the active list (+ n0 for the occlusion list).  vstate[p]: rounded disparity
+// index of a valid pixel (254 = outside [0,D)), -1 = invalid, -(slot+2) = invalid and pending in slot. ----
+__global__ void __launch_bounds__(256)
+k_vote_slots(AdcDims dm, const int* __restrict__ vlist, const int* __restrict__ counters, int* __restrict__ vstate,
+             int* __restrict__ pslotT, int* __restrict__ deg) {
+    const int pair = blockIdx.y;
+    const int n0 = counters[pair * ADC_CNT + 10], n1 = counters[pair * ADC_CNT + 11];
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n0 + n1; s += gridDim.x * blockDim.x) {
+        const int p = s < n0 ? vlist[((size_t)pair * 2 + 0) * dm.N + s] : vlist[((size_t)pair * 2 + 1) * dm.N + (s - n0)];
+        const int y = p / dm.W, x = p - y * dm.W;
+        vstate[(size_t)pair * dm.N + p] = -(s + 2);
+        pslotT[(size_t)pair * dm.N + (size_t)x * dm.H + y] = s;
+        deg[(size_t)pair * dm.N + s] = 0;
+    }
+}
+
+// ---- region scans: one warp per slot, one region row per lane (every lane streams its own row segment).
+//   FILL = false: histogram of the valid disparities -> hist[slot] (D counters packed two per 32-bit word; a region
+//                 holds < 65536 pixels), and deg[t]++ for every other pending pixel t of the region
+//   FILL = true : adjacency: slot is appended to the list of every such t
+template <bool FILL>
 __global__ void __launch_bounds__(VI_WARPS * 32)
-k_vote_init(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restrict__ alr_all,
-            const uint8_t* __restrict__ dq, const int* __restrict__ vlist, const int* __restrict__ counters,
-            unsigned* __restrict__ hist_all, long long hist_stride, int* __restrict__ pslotT_all) {
-    __shared__ int s_hist[VI_WARPS][VP_MAXD];
+k_vote_regions(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restrict__ alr_all,
+               const int* __restrict__ vstate_all, const int* __restrict__ vlist, const int* __restrict__ counters,
+               unsigned* __restrict__ hist_all, long long hist_stride, int* __restrict__ deg_all,
+               const int* __restrict__ off_all) {
+    __shared__ int s_hist[FILL ? 1 : VI_WARPS][FILL ? 1 : VP_MAXD];
     const AdcDims& dm = P.dm;
     const int pair = blockIdx.y;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int W = dm.W, H = dm.H, D = dm.D, HW = (D + 1) >> 1;
-    const int n0 = counters[pair * ADC_CNT + 10], n1 = counters[pair * ADC_CNT + 11];
+    const int W = dm.W, D = dm.D, HW = (D + 1) >> 1;
+    const int n0 = counters[pair * ADC_CNT + 10], n1 = counters[pair * ADC_CNT + 11], ns = n0 + n1;
+    if (FILL && counters[pair * ADC_CNT + 13] == 0) return;   // lists do not fit: this pair enumerates instead
     const uchar4* A = arms + (size_t)pair * dm.N;
     const uchar2* ALR = alr_all + (size_t)pair * dm.N;
-    const uint8_t* q2 = dq + (size_t)pair * 2 * dm.N;   // [2p] = rounded disparity index (255 = invalid, 254 = out of range)
+    const int* VS = vstate_all + (size_t)pair * dm.N;
     unsigned* hist = hist_all + (size_t)pair * hist_stride;
-    int* hs = s_hist[wid];
-    const int half = lane >> 4, sub = lane & 15;
-    for (int s = blockIdx.x * VI_WARPS + wid; s < n0 + n1; s += gridDim.x * VI_WARPS) {
+    int* adj = reinterpret_cast<int*>(hist + (size_t)ns * HW);   // adjacency entries follow the histograms
+    int* deg = deg_all + (size_t)pair * dm.N;                    // FILL: cursor of each list (starts at 0 again)
+    const int* off = off_all + (size_t)pair * (dm.N + 1);
+    int* hs = s_hist[FILL ? 0 : wid];
+    for (int s = blockIdx.x * VI_WARPS + wid; s < ns; s += gridDim.x * VI_WARPS) {
         const int p = s < n0 ? vlist[((size_t)pair * 2 + 0) * dm.N + s] : vlist[((size_t)pair * 2 + 1) * dm.N + (s - n0)];
         const int y = p / W, x = p - y * W;
-        for (int b = lane; b < D; b += 32) hs[b] = 0;
-        __syncwarp();
+        if (!FILL) {
+            for (int b = lane; b < D; b += 32) hs[b] = 0;
+            __syncwarp();
+        }
         const uchar4 a = __ldg(A + p);
         const int top = a.z, rows = top + (int)a.w + 1;
-        // two region rows per trip, one per half-warp; 16 columns per step
-        for (int r0 = 0; r0 < rows; r0 += 2) {
-            const int ri = r0 + half;
+        for (int r0 = 0; r0 < rows; r0 += 32) {
+            const int ri = r0 + lane;
+            int c = 1, c_hi = 0, rowi = 0;
             if (ri < rows) {
-                const int rowi = (y - top + ri) * W + x;
+                rowi = (y - top + ri) * W + x;
                 const uchar2 ar = __ldg(ALR + rowi);
-                for (int c = -(int)ar.x + sub; c <= (int)ar.y; c += 16) {
-                    const int v = q2[2 * (rowi + c)];
-                    if (v < D) atomicAdd(&hs[v], 1);
+                c = -(int)ar.x; c_hi = (int)ar.y;
+            }
+            for (; c <= c_hi; c++) {
+                const int v = __ldg(VS + rowi + c);
+                if (v >= 0) { if (!FILL && v < D) atomicAdd(&hs[v], 1); }
+                else if (v < -1) {
+                    const int t = -v - 2;
+                    if (t != s) {
+                        if (!FILL) atomicAdd(deg + t, 1);
+                        else adj[__ldg(off + t) + atomicAdd(deg + t, 1)] = s;
+                    }
                 }
             }
         }
-        __syncwarp();
-        for (int w2 = lane; w2 < HW; w2 += 32) {
-            const unsigned c0 = (unsigned)hs[2 * w2], c1 = (2 * w2 + 1 < D) ? (unsigned)hs[2 * w2 + 1] : 0u;
-            hist[(size_t)s * HW + w2] = c0 | (c1 << 16);
+        if (!FILL) {
+            __syncwarp();
+            for (int w2 = lane; w2 < HW; w2 += 32) {
+                const unsigned c0 = (unsigned)hs[2 * w2], c1 = (2 * w2 + 1 < D) ? (unsigned)hs[2 * w2 + 1] : 0u;
+                hist[(size_t)s * HW + w2] = c0 | (c1 << 16);
+            }
+            __syncwarp();
         }
-        if (lane == 0) pslotT_all[(size_t)pair * dm.N + (size_t)x * H + y] = s;
-        __syncwarp();
+    }
+}
+
+// ---- exclusive scan of the list lengths (one CTA per pair); decides whether the lists fit; resets the cursors ----
+__global__ void __launch_bounds__(1024)
+k_vote_offsets(AdcDims dm, int* __restrict__ counters, int* __restrict__ deg_all, int* __restrict__ off_all,
+               long long capacity_words, int force_enum) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int* cnt = counters + pair * ADC_CNT;
+    const int ns = cnt[10] + cnt[11], HW = (dm.D + 1) >> 1;
+    int* deg = deg_all + (size_t)pair * dm.N;
+    int* off = off_all + (size_t)pair * (dm.N + 1);
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    long long total = 0;
+    for (int i0 = 0; i0 < ns; i0 += 1024) {
+        const int i = i0 + tid;
+        const int v = i < ns ? deg[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        const int base = s_base;
+        if (i < ns) { off[i] = base + s_warp[wid] + inc - v; deg[i] = 0; }
+        __syncthreads();
+        if (tid == 1023) s_base = base + s_warp[31] + inc;
+        __syncthreads();
+        total = s_base;
+        if (total < 0 || total > 0x3fffffff) break;   // (uniform) far beyond any capacity
+    }
+    if (tid == 0) {
+        off[ns] = (int)total;
+        const bool fits = !force_enum && total >= 0 && total <= 0x3fffffff && (long long)ns * HW + total <= capacity_words;
+        cnt[13] = fits ? 1 : 0;
+        cnt[14] = (int)total;
     }
 }
 
 // One CTA per stereo pair.  Per-slot state (current vote, dirty / dead flags) lives in shared memory when the
 // lists fit (VP_SMEM_SLOTS slots; global memory otherwise -- one CTA = one SM, so plain accesses are coherent);
-// the histograms live in global memory and are read at L2 (ld.cg) because the pushes are L2 atomics; the arm
-// and slot tables are immutable during the kernel and go through the read-only path.
-// Everything that waits on memory is issued in batches of independent loads: a push first collects the
-// columns whose horizontal arm reaches the changed pixel, then tests the candidates of four columns x three
-// row groups at a time (12 loads in flight per lane, then up to 12 slot look-ups); a derive handles two
-// pixels per trip.  The first version walked the candidates one dependent L2 round trip after the other
-// and spent 17 us per change; the rounds themselves are cheap (CTA barriers).
+// the histograms live in global memory and are read at L2 (ld.cg) because the pushes are L2 atomics; the
+// adjacency lists and the fallback's arm / slot tables are immutable here and go through the read-only path.
 #define VP_SMEM_SLOTS 32768
 #define VP_FLAG_DIRTY 1
 #define VP_FLAG_DEAD 2
 
 __global__ void __launch_bounds__(VP_THREADS)
 k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __restrict__ atbT_all,
-            const int* __restrict__ pslotT_all, unsigned* hist_all, long long hist_stride, uint8_t* val_all,
-            uint8_t* flag_all, const int* __restrict__ vlist, int* counters, int* work_all, int2* chg_all,
+            const int* __restrict__ pslotT_all, unsigned* hist_all, long long hist_stride, const int* __restrict__ off_all,
+            uint8_t* val_all, uint8_t* flag_all, const int* __restrict__ vlist, int* counters, int* work_all, int2* chg_all,
             float* disp_old, float* disp_new, uint8_t* label, int cols_cap) {
     extern __shared__ __align__(16) unsigned char vp_smem[];
     __shared__ int s_nwork, s_nchg;
@@ -130,6 +209,7 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
     const uchar2* ATB = atbT_all + (size_t)pair * dm.N;
     const int* pslotT = pslotT_all + (size_t)pair * dm.N;
     unsigned* hist = hist_all + (size_t)pair * hist_stride;
+    const int* off = off_all + (size_t)pair * (dm.N + 1);
     int* work = work_all + (size_t)pair * dm.N;
     int2* chg = chg_all + (size_t)pair * dm.N;
     float* d_old = disp_old + (size_t)pair * dm.N;
@@ -137,29 +217,57 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
     uint8_t* lab = label + (size_t)pair * dm.N;
     int* cnt = counters + pair * ADC_CNT;
     const int n0 = __ldcg(cnt + 10), n1 = __ldcg(cnt + 11), ns = n0 + n1;
-    unsigned short* cols = reinterpret_cast<unsigned short*>(vp_smem) + (size_t)wid * cols_cap;   // per warp: hit columns of a push
+    const bool use_adj = __ldcg(cnt + 13) != 0;
+    const int* adj = reinterpret_cast<const int*>(hist + (size_t)ns * HW);
+    const int* list0 = vlist + ((size_t)pair * 2 + 0) * dm.N;
+    const int* list1 = vlist + ((size_t)pair * 2 + 1) * dm.N;
+    auto pix = [&](int s) { return s < n0 ? __ldg(list0 + s) : __ldg(list1 + (s - n0)); };
+    unsigned short* cols = reinterpret_cast<unsigned short*>(vp_smem) + (size_t)wid * cols_cap;   // fallback: hit columns of a push
     uint8_t* val;    // [slot] current vote, 255 = none
     uint8_t* flg;    // [slot] VP_FLAG_*
     if (ns <= VP_SMEM_SLOTS) {
         val = vp_smem + (size_t)VP_WARPS * cols_cap * 2;
         flg = val + VP_SMEM_SLOTS;
-        for (int i = tid; i < ns; i += VP_THREADS) { val[i] = 255; flg[i] = VP_FLAG_DIRTY; }
     } else {
         val = val_all + (size_t)pair * dm.N;
         flg = flag_all + (size_t)pair * dm.N;
-        for (int i = tid; i < ns; i += VP_THREADS) { val[i] = 255; flg[i] = VP_FLAG_DIRTY; }
     }
+    for (int i = tid; i < ns; i += VP_THREADS) { val[i] = 255; flg[i] = VP_FLAG_DIRTY; }
     __syncthreads();
     int rounds_total = 0, derives = 0, changes = 0;
 
-    // value change of pixel q (a -> b, 255 = invalid) -> histograms of the pending pixels whose region holds q.
-    //   phase 0 (inside the sweep of list k): pixels of list k that come after q in raster order
-    //   phase 1 (commit, a == 255):           pixels of list k before q, and every pixel of the other list
-    // Inverse region: p' = (px,py) has q = (qx,qy) in R(p') iff the horizontal arm of (px,qy) reaches qx and the
-    // vertical arm of (px,py) reaches qy.
-    auto push = [&](int q, int a, int b, int k, int phase) {
+    // value change of the pixel in slot t (a -> b, 255 = invalid) -> histograms of the pending pixels whose region
+    // holds it.
+    //   phase 0 (inside the sweep of list k): pixels of list k that come after it in raster order
+    //   phase 1 (commit, a == 255):           pixels of list k before it, and every pixel of the other list
+    auto touch = [&](int s, bool after, int a, int b, int k, int phase) {
+        const int f = flg[s];
+        if (f & VP_FLAG_DEAD) return;
+        const int kk = s >= n0 ? 1 : 0;
+        bool go;
+        if (phase == 0) go = kk == k && after;
+        else            go = (kk != k || !after) && val[s] == 255;   // (pixels filled by this very sweep are leaving)
+        if (!go) return;
+        unsigned* h = hist + (size_t)s * HW;
+        if (a < D) atomicSub(h + (a >> 1), 1u << ((a & 1) * 16));
+        if (b < D) atomicAdd(h + (b >> 1), 1u << ((b & 1) * 16));
+        if (!(f & VP_FLAG_DIRTY)) flg[s] = (uint8_t)VP_FLAG_DIRTY;   // (all writers write the same value)
+    };
+    auto push_adj = [&](int t, int q, int a, int b, int k, int phase) {
+        const int e0 = __ldg(off + t), e1 = __ldg(off + t + 1);
+        for (int e = e0 + lane; e < e1; e += 64) {
+            const int sA = __ldg(adj + e);
+            const int sB = e + 32 < e1 ? __ldg(adj + e + 32) : -1;
+            const int pA = pix(sA), pB = sB >= 0 ? pix(sB) : 0;
+            touch(sA, pA > q, a, b, k, phase);
+            if (sB >= 0) touch(sB, pB > q, a, b, k, phase);
+        }
+    };
+    // Fallback: inverse region by enumeration.  p' = (px,py) has q = (qx,qy) in R(p') iff the horizontal arm of
+    // (px,qy) reaches qx and the vertical arm of (px,py) reaches qy.  Columns first, then four columns x three row
+    // groups of candidates per trip (independent loads).
+    auto push_enum = [&](int q, int a, int b, int k, int phase) {
         const int qy = q / W, qx = q - qy * W;
-        // ---- columns px whose pixel (px, qy) reaches qx horizontally
         int ncols = 0;
         for (int c0 = 0; c0 < R; c0 += 32) {
             const int px_l = qx - L1 + c0 + lane;
@@ -173,7 +281,6 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
             ncols += __popc(m);
         }
         __syncwarp();
-        // ---- candidates (px, py), py in [qy - L1, qy + L1]: four columns x three row groups per trip
         for (int c = 0; c < ncols; c += 4) {
             int px[4];
 #pragma unroll
@@ -205,22 +312,8 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
                 for (int t = 0; t < 3; t++) {
                     const int py = qy - L1 + r0 + 32 * t + lane;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int s = slot[j][t];
-                        if (s < 0) continue;
-                        const int kk = s >= n0 ? 1 : 0;
-                        const bool after = py > qy || (py == qy && px[j] > qx);
-                        const int f = flg[s];
-                        if (f & VP_FLAG_DEAD) continue;
-                        bool go;
-                        if (phase == 0) go = kk == k && after;
-                        else            go = (kk != k || !after) && val[s] == 255;
-                        if (!go) continue;
-                        unsigned* h = hist + (size_t)s * HW;
-                        if (a < D) atomicSub(h + (a >> 1), 1u << ((a & 1) * 16));
-                        if (b < D) atomicAdd(h + (b >> 1), 1u << ((b & 1) * 16));
-                        if (!(f & VP_FLAG_DIRTY)) flg[s] = (uint8_t)VP_FLAG_DIRTY;   // (all writers write the same value)
-                    }
+                    for (int j = 0; j < 4; j++)
+                        if (slot[j][t] >= 0) touch(slot[j][t], py > qy || (py == qy && px[j] > qx), a, b, k, phase);
                 }
             }
         }
@@ -248,7 +341,6 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
         for (int k = 0; k < 2; k++) {
             const int n = k == 0 ? n0 : n1, base = k == 0 ? 0 : n0;
             if (n == 0) continue;
-            const int* list = vlist + ((size_t)pair * 2 + k) * dm.N;
             bool any_change = false;
             while (true) {
                 if (tid == 0) { s_nwork = 0; s_nchg = 0; }
@@ -259,10 +351,10 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
                     const bool d = i < n && (flg[base + i] & VP_FLAG_DIRTY);
                     if (d) flg[base + i] = 0;
                     const unsigned m = __ballot_sync(0xffffffffu, d);
-                    int off = 0;
-                    if (lane == 0 && m) off = atomicAdd(&s_nwork, __popc(m));
-                    off = __shfl_sync(0xffffffffu, off, 0);
-                    if (d) work[off + __popc(m & ((1u << lane) - 1u))] = i;
+                    int o = 0;
+                    if (lane == 0 && m) o = atomicAdd(&s_nwork, __popc(m));
+                    o = __shfl_sync(0xffffffffu, o, 0);
+                    if (d) work[o + __popc(m & ((1u << lane) - 1u))] = base + i;
                 }
                 __syncthreads();
                 const int nwork = s_nwork;
@@ -271,27 +363,27 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
                 // ---- derive: vote of every such pixel from its histogram, two pixels per trip
                 for (int t = 2 * wid; t < nwork; t += 2 * VP_WARPS) {
                     const bool two = t + 1 < nwork;
-                    const int iA = work[t], iB = two ? work[t + 1] : iA;
+                    const int sA = work[t], sB = two ? work[t + 1] : sA;
                     unsigned hA[4], hB[4];
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const int w2 = lane + 32 * j;
-                        hA[j] = (j < nhw && w2 < HW) ? __ldcg(hist + (size_t)(base + iA) * HW + w2) : 0u;
-                        hB[j] = (j < nhw && w2 < HW) ? __ldcg(hist + (size_t)(base + iB) * HW + w2) : 0u;
+                        hA[j] = (j < nhw && w2 < HW) ? __ldcg(hist + (size_t)sA * HW + w2) : 0u;
+                        hB[j] = (j < nhw && w2 < HW) ? __ldcg(hist + (size_t)sB * HW + w2) : 0u;
                     }
                     const int rA = vote(hA, nhw), rB = vote(hB, nhw);
                     if (lane == 0) {
                         derives += two ? 2 : 1;
-                        const int aA = val[base + iA];
+                        const int aA = val[sA];
                         if (rA != aA) {
-                            val[base + iA] = (uint8_t)rA;
-                            chg[atomicAdd(&s_nchg, 1)] = make_int2(__ldg(list + iA), aA | (rA << 8));
+                            val[sA] = (uint8_t)rA;
+                            chg[atomicAdd(&s_nchg, 1)] = make_int2(sA, aA | (rA << 8));
                         }
                         if (two) {
-                            const int aB = val[base + iB];
+                            const int aB = val[sB];
                             if (rB != aB) {
-                                val[base + iB] = (uint8_t)rB;
-                                chg[atomicAdd(&s_nchg, 1)] = make_int2(__ldg(list + iB), aB | (rB << 8));
+                                val[sB] = (uint8_t)rB;
+                                chg[atomicAdd(&s_nchg, 1)] = make_int2(sB, aB | (rB << 8));
                             }
                         }
                     }
@@ -304,7 +396,9 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
                 // ---- push the changes into the histograms of the later pixels of this list
                 for (int t = wid; t < nchg; t += VP_WARPS) {
                     const int2 c = chg[t];
-                    push(c.x, c.y & 255, (c.y >> 8) & 255, k, 0);
+                    const int q = pix(c.x);
+                    if (use_adj) push_adj(c.x, q, c.y & 255, (c.y >> 8) & 255, k, 0);
+                    else         push_enum(q, c.y & 255, (c.y >> 8) & 255, k, 0);
                 }
                 __syncthreads();
             }
@@ -319,28 +413,28 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
                 int v = 255;
                 if (i < n && !(flg[base + i] & VP_FLAG_DEAD)) { v = val[base + i]; f = v != 255; }
                 const unsigned m = __ballot_sync(0xffffffffu, f);
-                int off = 0;
-                if (lane == 0 && m) off = atomicAdd(&s_nchg, __popc(m));
-                off = __shfl_sync(0xffffffffu, off, 0);
+                int o = 0;
+                if (lane == 0 && m) o = atomicAdd(&s_nchg, __popc(m));
+                o = __shfl_sync(0xffffffffu, o, 0);
                 if (f) {
-                    const int p = __ldg(list + i);
+                    const int p = pix(base + i);
                     const float fv = (float)(v + dm.dmin);
                     d_old[p] = fv;
                     d_new[p] = fv;
                     lab[p] = 0;
-                    chg[off + __popc(m & ((1u << lane) - 1u))] = make_int2(p, base + i);
+                    chg[o + __popc(m & ((1u << lane) - 1u))] = make_int2(base + i, p);
                 }
             }
             __syncthreads();
             const int ncommit = s_nchg;
             changes += ncommit;
-            // (the filled pixels still count as pending here -- val != 255 keeps them out of the targets)
             for (int t = wid; t < ncommit; t += VP_WARPS) {
                 const int2 c = chg[t];
-                push(c.x, 255, (int)val[c.y], k, 1);
+                if (use_adj) push_adj(c.x, c.y, 255, (int)val[c.x], k, 1);
+                else         push_enum(c.y, 255, (int)val[c.x], k, 1);
             }
             __syncthreads();
-            for (int t = tid; t < ncommit; t += VP_THREADS) flg[chg[t].y] = (uint8_t)VP_FLAG_DEAD;
+            for (int t = tid; t < ncommit; t += VP_THREADS) flg[chg[t].x] = (uint8_t)VP_FLAG_DEAD;
             __syncthreads();
         }
     }
@@ -349,21 +443,29 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
     if (tid == 0) { __stcg(cnt + 2, rounds_total); __stcg(cnt + 12, changes); }
 }
 
-// returns false when the fast path does not apply (caller falls back to the pull kernels)
+// Expects the active lists (w.vlist, counters 10/11), w.vote_alr and w.vote_state (valid / invalid part, from
+// k_vote_encode).  Returns false when the fast path does not apply (caller falls back to the pull kernels).
 bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
     const AdcDims& dm = P.dm;
     const int L1 = P.L1 > 0 ? P.L1 : 0;
     if (dm.D > 254 || (2 * L1 + 1) * (2 * L1 + 1) > 65535) return false;
     if ((long long)dm.N * ((dm.D + 1) / 2) > dm.vol_stride) return false;   // histograms live in the idle cost volume
+    static int force_enum = -1;   // ADC_VOTE_ENUM=1: exercise the enumeration fallback (tests)
+    if (force_enum < 0) { const char* m = getenv("ADC_VOTE_ENUM"); force_enum = m ? atoi(m) : 0; }
     cudaMemsetAsync(w.vote_pslotT, 0xff, (size_t)w.S * dm.N * sizeof(int), st);
     dim3 tgrid((dm.W + 31) / 32, (dm.H + 31) / 32, w.S);
     k_vote_transpose<<<tgrid, 256, 0, st>>>(dm, w.arms, w.vote_atbT);
+    dim3 sgrid(64, w.S);
+    k_vote_slots<<<sgrid, 256, 0, st>>>(dm, w.vlist, w.counters, w.vote_state, w.vote_pslotT, w.vote_deg);
     unsigned* hist = reinterpret_cast<unsigned*>(w.volB);
     int gx = (148 * 8 + w.S - 1) / w.S;
     if (gx < 1) gx = 1;
     dim3 igrid(gx, w.S);
-    k_vote_init<<<igrid, VI_WARPS * 32, 0, st>>>(P, w.arms, w.vote_alr, w.vote_dq, w.vlist, w.counters, hist, dm.vol_stride,
-                                                 w.vote_pslotT);
+    k_vote_regions<false><<<igrid, VI_WARPS * 32, 0, st>>>(P, w.arms, w.vote_alr, w.vote_state, w.vlist, w.counters, hist,
+                                                           dm.vol_stride, w.vote_deg, w.vote_off);
+    k_vote_offsets<<<w.S, 1024, 0, st>>>(dm, w.counters, w.vote_deg, w.vote_off, dm.vol_stride, force_enum);
+    k_vote_regions<true><<<igrid, VI_WARPS * 32, 0, st>>>(P, w.arms, w.vote_alr, w.vote_state, w.vlist, w.counters, hist,
+                                                          dm.vol_stride, w.vote_deg, w.vote_off);
     const int cols_cap = (2 * L1 + 1 + 7) / 8 * 8;
     const size_t smem = (size_t)VP_WARPS * cols_cap * 2 + 2 * (size_t)VP_SMEM_SLOTS;
     static bool attr_done = false;
@@ -371,9 +473,9 @@ bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st,
         cudaFuncSetAttribute(k_vote_push, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done = true;
     }
-    k_vote_push<<<w.S, VP_THREADS, smem, st>>>(P, w.vote_alr, w.vote_atbT, w.vote_pslotT, hist, dm.vol_stride, w.vote_val,
-                                              w.vote_dirtyb, w.vlist, w.counters, w.last_eval, w.vote_dirty,
+    k_vote_push<<<w.S, VP_THREADS, smem, st>>>(P, w.vote_alr, w.vote_atbT, w.vote_pslotT, hist, dm.vol_stride, w.vote_off,
+                                              w.vote_val, w.vote_dirtyb, w.vlist, w.counters, w.last_eval, w.vote_dirty,
                                               w.disp_l, w.disp_t, w.label, cols_cap);
-    *launches += 3;
+    *launches += 6;
     return true;
 }

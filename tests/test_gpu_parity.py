@@ -221,3 +221,41 @@ def test_cpp_dropin_program_on_gpu(tmp_path):
     run = subprocess.run([str(exe)], capture_output=True, text=True)
     assert run.returncode == 0 and "DROPIN_OK" in run.stdout, (run.returncode, run.stdout[-500:], run.stderr[-500:])
     assert "cost aggregating! timing" in run.stdout     # the reference's six timing lines are kept
+
+
+def test_voting_enumeration_fallback(tmp_path):
+    """The voting kernel has two ways to find the histograms a filled pixel belongs to: precomputed adjacency lists
+    (default) and on-the-fly enumeration of the inverse cross region (when the lists would not fit).  The switch is
+    read once per process, so the fallback runs in a child: Cone and two synthetic cases through the VOTE stage and
+    the final map, against the oracle."""
+    import os, subprocess, sys, textwrap
+    script = tmp_path / "enum_case.py"
+    script.write_text(textwrap.dedent("""
+        import sys
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import numpy as np
+        import adc_testlib as T
+        import adcensus_b200 as A
+        cases = [T.load_cone() + (64,)]
+        for (w, h, D, seed) in ((120, 90, 48, 3), (97, 61, 24, 5)):
+            l, r = T.synthetic_pair(w, h, D, seed)
+            cases.append((l, r, D))
+        for left, right, D in cases:
+            h, w, _ = left.shape
+            opt = T.default_option(max_disparity=D)
+            orc = T.Oracle(w, h, opt)
+            eng = A.Engine(w, h, A.ADCensusOption(max_disparity=D))
+            orc.begin(left, right); orc.run_to("VOTE")
+            eng.debug_run(left, right, "VOTE")
+            assert eng.counters()[13] == 0, "adjacency lists were used although ADC_VOTE_ENUM=1"
+            for tap in ("DISP_L", "MISMATCHES", "OCCLUSIONS"):
+                g, o = eng.tap(tap), orc.tap(tap)
+                assert g.shape == o.shape and g.tobytes() == o.tobytes(), tap
+            want = orc.match(left, right)
+            assert eng.match(left, right).tobytes() == want.tobytes()
+            eng.close()
+        print("ok")
+    """ % (str(T.REPO), str(T.REPO / "tests"))))
+    env = dict(os.environ, ADC_VOTE_ENUM="1")
+    r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
