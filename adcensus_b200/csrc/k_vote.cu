@@ -20,12 +20,15 @@
 // them), so every derive sees a consistent histogram.
 //
 // Why: the pull form (re-scan R(p) whenever something near p changed) visits ~27 M pixels per Cone pair
-// behind a tile-granular "dirty" filter; the sequential reference 7.7 M.  Here the regions are scanned by
-// two batch-wide kernels (2.7 M visits each): the first builds the histograms and counts, for every pending
-// pixel t, how many regions contain it; the second writes those regions' owners into t's adjacency list
-// (CSR by target).  Only pending pixels ever change, so a value change of t is then: walk t's list (~40
-// entries, coalesced) and touch those histograms.  The iterative part -- 12.7 k value changes, 32 k 64-bin
-// derives, ~50 rounds -- fits one CTA per stereo pair with nothing but CTA barriers between rounds.
+// behind a tile-granular "dirty" filter; the sequential reference 7.7 M.  Here the regions are scanned
+// twice (2.7 M visits each): the first scan builds the histograms and counts, for every pending pixel t,
+// how many regions contain it; the second writes those regions' owners into t's adjacency list (CSR by
+// target; 2.1 M entries on Cone -- pending pixels come in blobs).  Only pending pixels ever change, so a
+// value change of t is then: walk t's list (coalesced) and touch those histograms.  All of it -- the two
+// scans with their counters and cursors in shared memory, then 12.7 k value changes, 32 k 64-bin derives,
+// ~50 rounds -- runs in ONE CTA per stereo pair with nothing but CTA barriers between the phases, beside
+// the bandwidth-bound kernels of the other lanes.  (Batch-wide scan kernels were tried first: their two
+// million global atomics per pair made them cost more whole-GPU time than the voting they prepared.)
 // If the adjacency lists do not fit the idle cost volume they live in (pathological inputs: huge regions
 // that are almost entirely invalid), the pair falls back to enumerating the inverse region of every change
 // on the fly from transposed arm tables (push_enum below).
@@ -63,7 +66,7 @@ k_vote_transpose(AdcDims dm, const uchar4* __restrict__ arms, uchar2* __restrict
 // index of a valid pixel (254 = outside [0,D)), -1 = invalid, -(slot+2) = invalid and pending in slot. ----
 __global__ void __launch_bounds__(256)
 k_vote_slots(AdcDims dm, const int* __restrict__ vlist, const int* __restrict__ counters, int* __restrict__ vstate,
-             int* __restrict__ pslotT, int* __restrict__ deg) {
+             int* __restrict__ pslotT) {
     const int pair = blockIdx.y;
     const int n0 = counters[pair * ADC_CNT + 10], n1 = counters[pair * ADC_CNT + 11];
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n0 + n1; s += gridDim.x * blockDim.x) {
@@ -71,117 +74,6 @@ k_vote_slots(AdcDims dm, const int* __restrict__ vlist, const int* __restrict__ 
         const int y = p / dm.W, x = p - y * dm.W;
         vstate[(size_t)pair * dm.N + p] = -(s + 2);
         pslotT[(size_t)pair * dm.N + (size_t)x * dm.H + y] = s;
-        deg[(size_t)pair * dm.N + s] = 0;
-    }
-}
-
-// ---- region scans: one warp per slot, one region row per lane (every lane streams its own row segment).
-//   FILL = false: histogram of the valid disparities -> hist[slot] (D counters packed two per 32-bit word; a region
-//                 holds < 65536 pixels), and deg[t]++ for every other pending pixel t of the region
-//   FILL = true : adjacency: slot is appended to the list of every such t
-template <bool FILL>
-__global__ void __launch_bounds__(VI_WARPS * 32)
-k_vote_regions(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restrict__ alr_all,
-               const int* __restrict__ vstate_all, const int* __restrict__ vlist, const int* __restrict__ counters,
-               unsigned* __restrict__ hist_all, long long hist_stride, int* __restrict__ deg_all,
-               const int* __restrict__ off_all) {
-    __shared__ int s_hist[FILL ? 1 : VI_WARPS][FILL ? 1 : VP_MAXD];
-    const AdcDims& dm = P.dm;
-    const int pair = blockIdx.y;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int W = dm.W, D = dm.D, HW = (D + 1) >> 1;
-    const int n0 = counters[pair * ADC_CNT + 10], n1 = counters[pair * ADC_CNT + 11], ns = n0 + n1;
-    if (FILL && counters[pair * ADC_CNT + 13] == 0) return;   // lists do not fit: this pair enumerates instead
-    const uchar4* A = arms + (size_t)pair * dm.N;
-    const uchar2* ALR = alr_all + (size_t)pair * dm.N;
-    const int* VS = vstate_all + (size_t)pair * dm.N;
-    unsigned* hist = hist_all + (size_t)pair * hist_stride;
-    int* adj = reinterpret_cast<int*>(hist + (size_t)ns * HW);   // adjacency entries follow the histograms
-    int* deg = deg_all + (size_t)pair * dm.N;                    // FILL: cursor of each list (starts at 0 again)
-    const int* off = off_all + (size_t)pair * (dm.N + 1);
-    int* hs = s_hist[FILL ? 0 : wid];
-    for (int s = blockIdx.x * VI_WARPS + wid; s < ns; s += gridDim.x * VI_WARPS) {
-        const int p = s < n0 ? vlist[((size_t)pair * 2 + 0) * dm.N + s] : vlist[((size_t)pair * 2 + 1) * dm.N + (s - n0)];
-        const int y = p / W, x = p - y * W;
-        if (!FILL) {
-            for (int b = lane; b < D; b += 32) hs[b] = 0;
-            __syncwarp();
-        }
-        const uchar4 a = __ldg(A + p);
-        const int top = a.z, rows = top + (int)a.w + 1;
-        for (int r0 = 0; r0 < rows; r0 += 32) {
-            const int ri = r0 + lane;
-            int c = 1, c_hi = 0, rowi = 0;
-            if (ri < rows) {
-                rowi = (y - top + ri) * W + x;
-                const uchar2 ar = __ldg(ALR + rowi);
-                c = -(int)ar.x; c_hi = (int)ar.y;
-            }
-            for (; c <= c_hi; c++) {
-                const int v = __ldg(VS + rowi + c);
-                if (v >= 0) { if (!FILL && v < D) atomicAdd(&hs[v], 1); }
-                else if (v < -1) {
-                    const int t = -v - 2;
-                    if (t != s) {
-                        if (!FILL) atomicAdd(deg + t, 1);
-                        else adj[__ldg(off + t) + atomicAdd(deg + t, 1)] = s;
-                    }
-                }
-            }
-        }
-        if (!FILL) {
-            __syncwarp();
-            for (int w2 = lane; w2 < HW; w2 += 32) {
-                const unsigned c0 = (unsigned)hs[2 * w2], c1 = (2 * w2 + 1 < D) ? (unsigned)hs[2 * w2 + 1] : 0u;
-                hist[(size_t)s * HW + w2] = c0 | (c1 << 16);
-            }
-            __syncwarp();
-        }
-    }
-}
-
-// ---- exclusive scan of the list lengths (one CTA per pair); decides whether the lists fit; resets the cursors ----
-__global__ void __launch_bounds__(1024)
-k_vote_offsets(AdcDims dm, int* __restrict__ counters, int* __restrict__ deg_all, int* __restrict__ off_all,
-               long long capacity_words, int force_enum) {
-    __shared__ int s_warp[32];
-    __shared__ int s_base;
-    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    int* cnt = counters + pair * ADC_CNT;
-    const int ns = cnt[10] + cnt[11], HW = (dm.D + 1) >> 1;
-    int* deg = deg_all + (size_t)pair * dm.N;
-    int* off = off_all + (size_t)pair * (dm.N + 1);
-    if (tid == 0) s_base = 0;
-    __syncthreads();
-    long long total = 0;
-    for (int i0 = 0; i0 < ns; i0 += 1024) {
-        const int i = i0 + tid;
-        const int v = i < ns ? deg[i] : 0;
-        int inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (lane == 31) s_warp[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            int w = s_warp[lane], wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
-            s_warp[lane] = wi - w;
-        }
-        __syncthreads();
-        const int base = s_base;
-        if (i < ns) { off[i] = base + s_warp[wid] + inc - v; deg[i] = 0; }
-        __syncthreads();
-        if (tid == 1023) s_base = base + s_warp[31] + inc;
-        __syncthreads();
-        total = s_base;
-        if (total < 0 || total > 0x3fffffff) break;   // (uniform) far beyond any capacity
-    }
-    if (tid == 0) {
-        off[ns] = (int)total;
-        const bool fits = !force_enum && total >= 0 && total <= 0x3fffffff && (long long)ns * HW + total <= capacity_words;
-        cnt[13] = fits ? 1 : 0;
-        cnt[14] = (int)total;
     }
 }
 
@@ -194,22 +86,24 @@ k_vote_offsets(AdcDims dm, int* __restrict__ counters, int* __restrict__ deg_all
 #define VP_FLAG_DEAD 2
 
 __global__ void __launch_bounds__(VP_THREADS)
-k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __restrict__ atbT_all,
-            const int* __restrict__ pslotT_all, unsigned* hist_all, long long hist_stride, const int* __restrict__ off_all,
-            uint8_t* val_all, uint8_t* flag_all, const int* __restrict__ vlist, int* counters, int* work_all, int2* chg_all,
-            float* disp_old, float* disp_new, uint8_t* label, int cols_cap) {
+k_vote_push(AdcParams P, const uchar4* __restrict__ arms_all, const uchar2* __restrict__ alr_all,
+            const uchar2* __restrict__ atbT_all, const int* __restrict__ pslotT_all, const int* __restrict__ vstate_all,
+            unsigned* hist_all, long long hist_stride, int* cur_all, uint8_t* val_all, uint8_t* flag_all,
+            const int* __restrict__ vlist, int* counters, int* work_all, int2* chg_all,
+            float* disp_old, float* disp_new, uint8_t* label, int cols_cap, int slot_cap, int force_enum) {
     extern __shared__ __align__(16) unsigned char vp_smem[];
-    __shared__ int s_nwork, s_nchg;
+    __shared__ int s_nwork, s_nchg, s_warp[32], s_base, s_fits;
     const AdcDims& dm = P.dm;
     const int pair = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int W = dm.W, H = dm.H, D = dm.D, HW = (D + 1) >> 1;
     const int L1 = max(P.L1, 0), R = 2 * L1 + 1;
+    const uchar4* A = arms_all + (size_t)pair * dm.N;
     const uchar2* ALR = alr_all + (size_t)pair * dm.N;
     const uchar2* ATB = atbT_all + (size_t)pair * dm.N;
     const int* pslotT = pslotT_all + (size_t)pair * dm.N;
+    const int* VS = vstate_all + (size_t)pair * dm.N;
     unsigned* hist = hist_all + (size_t)pair * hist_stride;
-    const int* off = off_all + (size_t)pair * (dm.N + 1);
     int* work = work_all + (size_t)pair * dm.N;
     int2* chg = chg_all + (size_t)pair * dm.N;
     float* d_old = disp_old + (size_t)pair * dm.N;
@@ -217,24 +111,120 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
     uint8_t* lab = label + (size_t)pair * dm.N;
     int* cnt = counters + pair * ADC_CNT;
     const int n0 = __ldcg(cnt + 10), n1 = __ldcg(cnt + 11), ns = n0 + n1;
-    const bool use_adj = __ldcg(cnt + 13) != 0;
-    const int* adj = reinterpret_cast<const int*>(hist + (size_t)ns * HW);
+    int* adj = reinterpret_cast<int*>(hist + (size_t)ns * HW);   // adjacency entries follow the histograms
     const int* list0 = vlist + ((size_t)pair * 2 + 0) * dm.N;
     const int* list1 = vlist + ((size_t)pair * 2 + 1) * dm.N;
     auto pix = [&](int s) { return s < n0 ? __ldg(list0 + s) : __ldg(list1 + (s - n0)); };
-    unsigned short* cols = reinterpret_cast<unsigned short*>(vp_smem) + (size_t)wid * cols_cap;   // fallback: hit columns of a push
+    // shared memory: [fallback column lists][per-warp histogram of the first scan][val][flg][cur]
+    unsigned short* cols = reinterpret_cast<unsigned short*>(vp_smem) + (size_t)wid * cols_cap;
+    const int hist_cap = (D + 31) & ~31;
+    int* whist = reinterpret_cast<int*>(vp_smem + (size_t)VP_WARPS * cols_cap * 2) + (size_t)wid * hist_cap;
+    unsigned char* after_hist = vp_smem + (size_t)VP_WARPS * cols_cap * 2 + (size_t)VP_WARPS * hist_cap * 4;
     uint8_t* val;    // [slot] current vote, 255 = none
     uint8_t* flg;    // [slot] VP_FLAG_*
-    if (ns <= VP_SMEM_SLOTS) {
-        val = vp_smem + (size_t)VP_WARPS * cols_cap * 2;
-        flg = val + VP_SMEM_SLOTS;
+    int* cur;        // [slot + 1] list lengths -> list starts -> fill cursors (= list ends once filled)
+    const bool state_smem = ns <= slot_cap;
+    if (state_smem) {
+        val = after_hist;
+        flg = val + slot_cap;
+        cur = reinterpret_cast<int*>(flg + slot_cap);
     } else {
         val = val_all + (size_t)pair * dm.N;
         flg = flag_all + (size_t)pair * dm.N;
+        cur = cur_all + (size_t)pair * (dm.N + 1);
     }
     for (int i = tid; i < ns; i += VP_THREADS) { val[i] = 255; flg[i] = VP_FLAG_DIRTY; }
+    for (int i = tid; i <= ns; i += VP_THREADS) cur[i] = 0;
     __syncthreads();
     int rounds_total = 0, derives = 0, changes = 0;
+
+    // ---- region scan of slot s by one warp: two region rows per trip (one per half-warp), 16 columns per step; the
+    //      horizontal arms of all rows are fetched up front (lane r holds rows r, r+32, r+64) and handed out by shuffle
+    auto scan_region = [&](int s, auto&& visit) {
+        const int p = pix(s);
+        const int y = p / W, x = p - y * W;
+        const uchar4 a = __ldg(A + p);
+        const int top = a.z, rows = top + (int)a.w + 1;
+        const int rbase = (y - top) * W + x;
+        unsigned ar[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int ri = lane + 32 * j;
+            uchar2 v = make_uchar2(0, 0);
+            if (ri < rows) v = __ldg(ALR + rbase + ri * W);
+            ar[j] = (unsigned)v.x | ((unsigned)v.y << 8);
+        }
+        const int half = lane >> 4, sub = lane & 15;
+        for (int r0 = 0; r0 < rows; r0 += 2) {
+            const int ri = r0 + half;
+            unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
+            if (rows > 32) {
+                const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31), a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
+                a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
+            }
+            if (ri < rows) {
+                const int rowi = rbase + ri * W, c_hi = (int)(a2 >> 8);
+                for (int c = -(int)(a2 & 255u) + sub; c <= c_hi; c += 16) visit(__ldg(VS + rowi + c));
+            }
+        }
+    };
+
+    // ---- scan 1: histograms (packed two counters per word; a region holds < 65536 pixels) and list lengths
+    for (int s = wid; s < ns; s += VP_WARPS) {
+        for (int b = lane; b < D; b += 32) whist[b] = 0;
+        __syncwarp();
+        scan_region(s, [&](int v) {
+            if (v >= 0) { if (v < D) atomicAdd(&whist[v], 1); }
+            else if (v < -1 && -v - 2 != s) atomicAdd(&cur[-v - 1], 1);   // length of t's list, kept at index t + 1
+        });
+        __syncwarp();
+        for (int w2 = lane; w2 < HW; w2 += 32) {
+            const unsigned c0 = (unsigned)whist[2 * w2], c1 = (2 * w2 + 1 < D) ? (unsigned)whist[2 * w2 + 1] : 0u;
+            hist[(size_t)s * HW + w2] = c0 | (c1 << 16);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- inclusive prefix sum over cur[0..ns]: cur[t] = start of t's list, cur[ns] = number of entries
+    if (tid == 0) { s_base = 0; s_fits = 1; }
+    __syncthreads();
+    for (int i0 = 0; i0 <= ns; i0 += VP_THREADS) {
+        const int i = i0 + tid;
+        const int v = i <= ns ? (state_smem ? cur[i] : __ldcg(cur + i)) : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const int w = s_warp[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        const int base = s_base;
+        if (i <= ns) cur[i] = base + s_warp[wid] + inc;
+        __syncthreads();
+        if (tid == VP_THREADS - 1) {
+            const long long nb = (long long)base + s_warp[VP_WARPS - 1] + inc;
+            if (nb > 0x3fffffff) s_fits = 0;
+            s_base = (int)min(nb, (long long)0x3fffffff);
+        }
+        __syncthreads();
+    }
+    const int n_adj = s_base;
+    const bool use_adj = !force_enum && s_fits && (long long)ns * HW + n_adj <= hist_stride;
+    // ---- scan 2: the lists themselves (afterwards cur[t] = end of t's list = start of t + 1's)
+    if (use_adj) {
+        for (int s = wid; s < ns; s += VP_WARPS)
+            scan_region(s, [&](int v) {
+                if (v < -1 && -v - 2 != s) adj[atomicAdd(&cur[-v - 2], 1)] = s;
+            });
+    }
+    __syncthreads();
+    if (tid == 0) { __stcg(cnt + 13, use_adj ? 1 : 0); __stcg(cnt + 14, n_adj); }
 
     // value change of the pixel in slot t (a -> b, 255 = invalid) -> histograms of the pending pixels whose region
     // holds it.
@@ -254,10 +244,11 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all, const uchar2* __res
         if (!(f & VP_FLAG_DIRTY)) flg[s] = (uint8_t)VP_FLAG_DIRTY;   // (all writers write the same value)
     };
     auto push_adj = [&](int t, int q, int a, int b, int k, int phase) {
-        const int e0 = __ldg(off + t), e1 = __ldg(off + t + 1);
+        // (global-memory cursors were advanced by L2 atomics: read them at L2)
+        const int e0 = t > 0 ? (state_smem ? cur[t - 1] : __ldcg(cur + t - 1)) : 0, e1 = state_smem ? cur[t] : __ldcg(cur + t);
         for (int e = e0 + lane; e < e1; e += 64) {
-            const int sA = __ldg(adj + e);
-            const int sB = e + 32 < e1 ? __ldg(adj + e + 32) : -1;
+            const int sA = adj[e];
+            const int sB = e + 32 < e1 ? adj[e + 32] : -1;
             const int pA = pix(sA), pB = sB >= 0 ? pix(sB) : 0;
             touch(sA, pA > q, a, b, k, phase);
             if (sB >= 0) touch(sB, pB > q, a, b, k, phase);
@@ -456,26 +447,25 @@ bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st,
     dim3 tgrid((dm.W + 31) / 32, (dm.H + 31) / 32, w.S);
     k_vote_transpose<<<tgrid, 256, 0, st>>>(dm, w.arms, w.vote_atbT);
     dim3 sgrid(64, w.S);
-    k_vote_slots<<<sgrid, 256, 0, st>>>(dm, w.vlist, w.counters, w.vote_state, w.vote_pslotT, w.vote_deg);
+    k_vote_slots<<<sgrid, 256, 0, st>>>(dm, w.vlist, w.counters, w.vote_state, w.vote_pslotT);
     unsigned* hist = reinterpret_cast<unsigned*>(w.volB);
-    int gx = (148 * 8 + w.S - 1) / w.S;
-    if (gx < 1) gx = 1;
-    dim3 igrid(gx, w.S);
-    k_vote_regions<false><<<igrid, VI_WARPS * 32, 0, st>>>(P, w.arms, w.vote_alr, w.vote_state, w.vlist, w.counters, hist,
-                                                           dm.vol_stride, w.vote_deg, w.vote_off);
-    k_vote_offsets<<<w.S, 1024, 0, st>>>(dm, w.counters, w.vote_deg, w.vote_off, dm.vol_stride, force_enum);
-    k_vote_regions<true><<<igrid, VI_WARPS * 32, 0, st>>>(P, w.arms, w.vote_alr, w.vote_state, w.vlist, w.counters, hist,
-                                                          dm.vol_stride, w.vote_deg, w.vote_off);
     const int cols_cap = (2 * L1 + 1 + 7) / 8 * 8;
-    const size_t smem = (size_t)VP_WARPS * cols_cap * 2 + 2 * (size_t)VP_SMEM_SLOTS;
+    // shared memory: column lists (fallback), one histogram per warp, then val / flg / cur for as many slots as fit
+    const size_t fixed = (size_t)VP_WARPS * cols_cap * 2 + (size_t)VP_WARPS * ((dm.D + 31) & ~31) * 4;
+    int slot_cap = (int)((220 * 1024 - fixed - 16) / 6) & ~15;
+    if (slot_cap > VP_SMEM_SLOTS) slot_cap = VP_SMEM_SLOTS;
+    static int cap_override = -1;   // ADC_VOTE_SLOTCAP: shrink the shared-memory slot capacity (tests of the global-memory state)
+    if (cap_override < 0) { const char* m = getenv("ADC_VOTE_SLOTCAP"); cap_override = m ? atoi(m) : 0; }
+    if (cap_override > 0 && cap_override < slot_cap) slot_cap = cap_override & ~15;
+    const size_t smem = fixed + 2 * (size_t)slot_cap + ((size_t)slot_cap + 1) * 4;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_vote_push, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_vote_push, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done = true;
     }
-    k_vote_push<<<w.S, VP_THREADS, smem, st>>>(P, w.vote_alr, w.vote_atbT, w.vote_pslotT, hist, dm.vol_stride, w.vote_off,
-                                              w.vote_val, w.vote_dirtyb, w.vlist, w.counters, w.last_eval, w.vote_dirty,
-                                              w.disp_l, w.disp_t, w.label, cols_cap);
-    *launches += 6;
+    k_vote_push<<<w.S, VP_THREADS, smem, st>>>(P, w.arms, w.vote_alr, w.vote_atbT, w.vote_pslotT, w.vote_state, hist,
+                                              dm.vol_stride, w.vote_off, w.vote_val, w.vote_dirtyb, w.vlist, w.counters,
+                                              w.last_eval, w.vote_dirty, w.disp_l, w.disp_t, w.label, cols_cap, slot_cap, force_enum);
+    *launches += 3;
     return true;
 }

@@ -1,6 +1,7 @@
 // k_wta.cu -- stage 4: winner-takes-all with parabola refinement for the left view and, from the
 // same volume, for the right view (reference: ADCensusStereo.cpp:188-243 and :245-310).
 #include "adc_common.cuh"
+#include <stdlib.h>
 
 // Parabola through (best-1, best, best+1), ADCensusStereo.cpp:234-240.  Explicit _rn intrinsics keep
 // nvcc from contracting c1 + c2 - 2*min into an FMA.
@@ -109,6 +110,129 @@ k_wta_right_finish(AdcDims dm, const float* __restrict__ vol, const unsigned lon
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row-walking kernel (default for D <= 256).  k_wta_tile below turned out to be bound by instruction issue
+// (one thread per pixel scanning its D costs one by one out of shared memory, ~1400 thread instructions per
+// pixel for the two views).  Here a warp walks along an image row, lane = disparity:
+//   left view : the pixel's D costs sit in the lanes (d = lane + 32 j); non-negative floats order like their
+//               bit patterns, so the minimum is one REDUX.MIN and "first minimum wins" is the lowest set bit of a
+//               ballot (ADCensusStereo.cpp:211-222 -- a cost that is not below Large_Float is never taken);
+//   right view: cost_R(xr, d) = cost_L(xr + d + dmin, d) (:262-287).  Lane d holds the running (min, argmin) of the
+//               right pixel xr = x - dmin - d it currently serves; when the walk advances to x + 1 that right pixel
+//               is served by lane d + 1, so the running pairs move up one lane per step (a systolic chain through the
+//               warp, 32 disparities per register; the last lane of chain j feeds lane 0 of chain j + 1).  A right
+//               pixel leaves the chain complete at d = D - 1.  Columns outside the image simply contribute
+//               nothing, as in the reference, and the walk runs D - 1 steps past the row end to drain the chain.
+// Every cost is read exactly once, coalesced (the two parabola neighbours of each view are re-read from L1/L2).
+// ---------------------------------------------------------------------------------------------
+template <int NCH>   // NCH = ceil(D / 32) chains
+__global__ void __launch_bounds__(128)
+k_wta_walk(AdcDims dm, int n_pairs, int seg_len, int n_seg, const float* __restrict__ vol, float* __restrict__ disp_l,
+           float* __restrict__ disp_r) {
+    const int lane = threadIdx.x & 31;
+    long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int y = (int)(gw % dm.H); gw /= dm.H;
+    const int seg = (int)(gw % n_seg);
+    const int pair = (int)(gw / n_seg);
+    if (pair >= n_pairs) return;
+    const int W = dm.W, D = dm.D, Dp = dm.Dp, dmin = dm.dmin;
+    const int a = seg * seg_len, b = min(W, a + seg_len);            // this warp's output columns (both views)
+    const float* rowv = vol + (size_t)pair * dm.vol_stride + (size_t)y * W * Dp;
+    float* out_l = disp_l + (size_t)pair * dm.N + (size_t)y * W;
+    float* out_r = disp_r + (size_t)pair * dm.N + (size_t)y * W;
+    const unsigned LARGE_BITS = __float_as_uint(ADC_LARGE_F);
+    // the right pixels a..b-1 collect their candidates at x = xr + dmin + d, d = 0..D-1; the left outputs need x = a..b-1
+    const int x_begin = min(a, a + dmin), x_end = max(b - 1, b - 1 + dmin + D - 1);
+    float rc[NCH];      // running minimum of the right pixel served by (chain j, this lane)
+    int rb[NCH];        // its disparity index
+#pragma unroll
+    for (int j = 0; j < NCH; j++) { rc[j] = ADC_LARGE_F; rb[j] = -1; }
+    const int last_j = (D - 1) >> 5, last_lane = (D - 1) & 31;
+    for (int x = x_begin; x <= x_end; x++) {
+        const bool inside = x >= 0 && x < W;
+        float c[NCH];
+#pragma unroll
+        for (int j = 0; j < NCH; j++) {
+            const int d = lane + 32 * j;
+            c[j] = (inside && d < D) ? __ldg(rowv + (size_t)x * Dp + d) : ADC_INVALID_F;
+        }
+        // ---- right view: shift the chains one lane up, then merge this column's candidates
+        float carry_c = ADC_LARGE_F;   // enters lane 0 of chain 0: a fresh right pixel
+        int carry_b = -1;
+#pragma unroll
+        for (int j = 0; j < NCH; j++) {
+            const float tc = __shfl_sync(0xffffffffu, rc[j], (lane + 31) & 31);
+            const int tb = __shfl_sync(0xffffffffu, rb[j], (lane + 31) & 31);
+            rc[j] = lane == 0 ? carry_c : tc;
+            rb[j] = lane == 0 ? carry_b : tb;
+            carry_c = tc; carry_b = tb;              // (only lane 0's copy is used: it received lane 31's pair)
+            if (inside && lane + 32 * j < D && rc[j] > c[j]) { rc[j] = c[j]; rb[j] = lane + 32 * j; }   // strict '>'
+        }
+        // the right pixel that just took its last candidate (d = D - 1)
+        {
+            const int xr = x - dmin - (D - 1);
+            if (xr >= a && xr < b && lane == last_lane) {
+                float rcl = rc[0];
+                int rbl = rb[0];
+#pragma unroll
+                for (int j = 1; j < NCH; j++) if (j == last_j) { rcl = rc[j]; rbl = rb[j]; }
+                // best starts at 0 (not dmin) when no column was valid, as in the reference (:271)
+                const int best = rbl >= 0 ? dmin + rbl : 0;
+                const float best_cost = rbl >= 0 ? rcl : ADC_LARGE_F;
+                float o = (float)best;
+                const int i1 = best - 1 - dmin, i2 = best + 1 - dmin;
+                if (best != dmin && best != dm.dmax - 1 && i1 >= 0 && i2 < D) {
+                    const int x1 = xr + best - 1, x2 = xr + best + 1;
+                    const float c1 = (x1 >= 0 && x1 < W) ? __ldg(rowv + (size_t)x1 * Dp + i1) : ADC_LARGE_F;   // (:277-286)
+                    const float c2 = (x2 >= 0 && x2 < W) ? __ldg(rowv + (size_t)x2 * Dp + i2) : ADC_LARGE_F;
+                    o = adc_subpixel(c1, c2, best_cost, best);
+                }
+                out_r[xr] = o;
+            }
+        }
+        // ---- left view of column x
+        if (x >= a && x < b) {
+            unsigned um = 0xffffffffu;
+#pragma unroll
+            for (int j = 0; j < NCH; j++) um = min(um, (lane + 32 * j < D) ? __float_as_uint(c[j]) : 0xffffffffu);
+            const unsigned m = __reduce_min_sync(0xffffffffu, um);
+            int best = 0;                                 // stays 0 when no cost is below Large_Float (:209, :218)
+            float best_cost = ADC_LARGE_F;
+            if (m < LARGE_BITS) {
+                int di = -1;
+#pragma unroll
+                for (int j = 0; j < NCH; j++) {
+                    const unsigned bal = __ballot_sync(0xffffffffu, lane + 32 * j < D && __float_as_uint(c[j]) == m);
+                    if (di < 0 && bal) di = 32 * j + __ffs(bal) - 1;
+                }
+                best = dmin + di;
+                best_cost = __uint_as_float(m);
+            }
+            if (lane == 0) {
+                float o = ADC_INVALID_F;
+                const int i1 = best - 1 - dmin, i2 = best + 1 - dmin;
+                if (best != dmin && best != dm.dmax - 1 && i1 >= 0 && i2 < D) {
+                    const float* v = rowv + (size_t)x * Dp;
+                    o = adc_subpixel(__ldg(v + i1), __ldg(v + i2), best_cost, best);
+                }
+                out_l[x] = o;
+            }
+        }
+    }
+}
+
+template <int NCH>
+static void launch_wta_walk(const AdcParams& P, const AdcWave& w, const float* vol, cudaStream_t st) {
+    const long long rows = (long long)w.S * P.dm.H;
+    int n_seg = (int)((148 * 40 + rows / 2) / rows);          // ~40 warps per SM over the whole launch
+    if (n_seg < 1) n_seg = 1;
+    if (n_seg > (P.dm.W + 63) / 64) n_seg = (P.dm.W + 63) / 64;
+    const int seg_len = (P.dm.W + n_seg - 1) / n_seg;
+    n_seg = (P.dm.W + seg_len - 1) / seg_len;
+    const long long warps = rows * n_seg;
+    k_wta_walk<NCH><<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(P.dm, w.S, seg_len, n_seg, vol, w.disp_l, w.disp_r);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fast path (Dp <= 192): no atomics.  A CTA stages the costs of WT_PX + D - 1 neighbouring columns of
 // one row in shared memory (coalesced 128-bit loads, row stride Dp+1 words so that both scans below
 // are bank-conflict free), then one thread per pixel scans d = 0..D-1 sequentially -- for the left
@@ -189,6 +313,22 @@ k_wta_tile(AdcDims dm, int wpx, const float* __restrict__ vol, float* __restrict
 }
 
 int adc_launch_wta(const AdcParams& P, const AdcWave& w, const float* vol, cudaStream_t st, unsigned long long* launches) {
+    static int mode = -1;   // development switch ADC_WTA_MODE: 1 = row-walking kernel (default), 0 = tile / atomic kernels
+    if (mode < 0) { const char* m = getenv("ADC_WTA_MODE"); mode = m ? atoi(m) : 1; }
+    if (mode == 1 && P.dm.D <= 256) {
+        switch ((P.dm.D + 31) / 32) {
+            case 1: launch_wta_walk<1>(P, w, vol, st); break;
+            case 2: launch_wta_walk<2>(P, w, vol, st); break;
+            case 3: launch_wta_walk<3>(P, w, vol, st); break;
+            case 4: launch_wta_walk<4>(P, w, vol, st); break;
+            case 5: launch_wta_walk<5>(P, w, vol, st); break;
+            case 6: launch_wta_walk<6>(P, w, vol, st); break;
+            case 7: launch_wta_walk<7>(P, w, vol, st); break;
+            default: launch_wta_walk<8>(P, w, vol, st); break;
+        }
+        ++*launches;
+        return 0;
+    }
     const int extra = (P.dm.dmax - 1 > 0 ? P.dm.dmax - 1 : 0) - (P.dm.dmin < 0 ? P.dm.dmin : 0);
     int wpx = 128;                                   // output pixels per CTA: as many as keep the tile small
     while (wpx > 32 && (size_t)(wpx + extra) * (P.dm.Dp + 1) * sizeof(float) > 64 * 1024) wpx >>= 1;

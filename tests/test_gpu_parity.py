@@ -223,11 +223,14 @@ def test_cpp_dropin_program_on_gpu(tmp_path):
     assert "cost aggregating! timing" in run.stdout     # the reference's six timing lines are kept
 
 
-def test_voting_enumeration_fallback(tmp_path):
-    """The voting kernel has two ways to find the histograms a filled pixel belongs to: precomputed adjacency lists
+@pytest.mark.parametrize("env", [{"ADC_VOTE_ENUM": "1"}, {"ADC_VOTE_SLOTCAP": "256"}], ids=["enumeration", "global-state"])
+def test_voting_fallback_paths(tmp_path, env):
+    """(enumeration) The voting kernel has two ways to find the histograms a filled pixel belongs to: precomputed adjacency lists
     (default) and on-the-fly enumeration of the inverse cross region (when the lists would not fit).  The switch is
     read once per process, so the fallback runs in a child: Cone and two synthetic cases through the VOTE stage and
-    the final map, against the oracle."""
+    the final map, against the oracle.
+    (global-state) Per-slot state lives in shared memory when the lists fit, else in global memory; a tiny capacity forces
+    the latter."""
     import os, subprocess, sys, textwrap
     script = tmp_path / "enum_case.py"
     script.write_text(textwrap.dedent("""
@@ -247,7 +250,7 @@ def test_voting_enumeration_fallback(tmp_path):
             eng = A.Engine(w, h, A.ADCensusOption(max_disparity=D))
             orc.begin(left, right); orc.run_to("VOTE")
             eng.debug_run(left, right, "VOTE")
-            assert eng.counters()[13] == 0, "adjacency lists were used although ADC_VOTE_ENUM=1"
+            assert eng.counters()[13] == (0 if %r else 1), "wrong adjacency / enumeration path"
             for tap in ("DISP_L", "MISMATCHES", "OCCLUSIONS"):
                 g, o = eng.tap(tap), orc.tap(tap)
                 assert g.shape == o.shape and g.tobytes() == o.tobytes(), tap
@@ -255,7 +258,7 @@ def test_voting_enumeration_fallback(tmp_path):
             assert eng.match(left, right).tobytes() == want.tobytes()
             eng.close()
         print("ok")
-    """ % (str(T.REPO), str(T.REPO / "tests"))))
-    env = dict(os.environ, ADC_VOTE_ENUM="1")
+    """ % (str(T.REPO), str(T.REPO / "tests"), "ADC_VOTE_ENUM" in env)))
+    env = dict(os.environ, **env)
     r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
