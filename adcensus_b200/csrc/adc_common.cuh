@@ -74,7 +74,7 @@ struct AdcWave {            // device pointers of one wave (S pairs)
     int* counters;          // [S][ADC_CNT]: 0,1 list sizes; 2 voting rounds; 3 voting evaluations; 4.. flags/queues
     int* rowcnt;            // [S][2][H] per-row list counts / offsets
     unsigned* so_bitrows;   // [S][4][H][row words] mirrored per-row bit vectors of the right image (scanline optimiser)
-    unsigned* so_rec;       // [S][N][rec words] per-pixel penalty records of the pass being run
+    unsigned* so_rec;       // [S][4][N][rec words] per-pixel penalty records of the four pass directions
     int* tile_stamp;        // [S][tiles] region voting: epoch of the last change near a 16x16 tile
     int* last_eval;         // [S][N]     region voting: epoch of a pixel's (or tile's) last evaluation
     unsigned long long* wta_key;  // [S][N] right-view WTA keys (ordered cost << 32 | disparity index)

@@ -96,19 +96,22 @@ k_so_bitrows(AdcDims dm, int tso, const uint8_t* __restrict__ dmap, unsigned* __
 // per-pixel record for one pass direction: word 0 = (d1 < tso), words 1.. = bit d -> (d2(d) < tso)
 __host__ __device__ inline int so_rec_words(int Dp) { return ((1 + (Dp + 31) / 32 + 1) + 3) / 4 * 4; }
 
+// (one launch writes the records of all four pass directions, blockIdx.z = direction)
 __global__ void __launch_bounds__(256)
-k_so_records(AdcDims dm, int tso, int sx, int sy, const uint8_t* __restrict__ dmap,
+k_so_records(AdcDims dm, int tso, const uint8_t* __restrict__ dmap,
              const unsigned* __restrict__ bitrows, unsigned* __restrict__ rec) {
     const int pair = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dm.N) return;
+    const int sx = blockIdx.z == 0 ? 1 : (blockIdx.z == 1 ? -1 : 0);
+    const int sy = blockIdx.z == 2 ? 1 : (blockIdx.z == 3 ? -1 : 0);
     const int W = dm.W, D = dm.D, dmin = dm.dmin;
     const int y = i / W, x = i - y * W;
     const bool fwd = (sx + sy) > 0;
     const int pstep = sx + sy * W;
     const int variant = sx ? (fwd ? 0 : 1) : (fwd ? 2 : 3);
     const int rw = so_row_words(W), nrec = so_rec_words(dm.Dp);
-    unsigned* out = rec + ((size_t)pair * dm.N + i) * nrec;
+    unsigned* out = rec + (((size_t)pair * 4 + variant) * dm.N + i) * nrec;
     // d1: this pixel vs the one the path came from (undefined for path heads, which never use it)
     const uint8_t* ml = dmap + ((size_t)pair * 4 + (sx ? 0 : 1)) * dm.N;
     const int pi_from = i - pstep;
@@ -130,21 +133,22 @@ k_so_records(AdcDims dm, int tso, int sx, int sy, const uint8_t* __restrict__ dm
     };
     unsigned fill_hi = a1;
     if (lo <= hi) fill_hi = (window(hi) & 1u) ? 0xffffffffu : 0u;
-    out[0] = a1;
     const int nw = (dm.Dp + 31) / 32 + 1;
-    for (int w0 = 0; w0 < nw; w0++) {
-        unsigned v;
-        if (lo > hi) v = a1;
-        else {
-            const int d0 = w0 * 32;
-            const unsigned raw = window(d0);
-            // masks of the bits with d < lo and d > hi inside this word
-            const unsigned m_lo = lo <= d0 ? 0u : (lo >= d0 + 32 ? 0xffffffffu : ((1u << (lo - d0)) - 1u));
-            const unsigned m_hi = hi >= d0 + 31 ? 0u : (hi < d0 ? 0xffffffffu : ~((2u << (hi - d0)) - 1u));
-            v = (raw & ~m_lo & ~m_hi) | (a1 & m_lo) | (fill_hi & m_hi);
-        }
-        out[1 + w0] = v;
+    auto word = [&](int w0) -> unsigned {
+        if (lo > hi) return a1;
+        const int d0 = w0 * 32;
+        const unsigned raw = window(d0);
+        // masks of the bits with d < lo and d > hi inside this word
+        const unsigned m_lo = lo <= d0 ? 0u : (lo >= d0 + 32 ? 0xffffffffu : ((1u << (lo - d0)) - 1u));
+        const unsigned m_hi = hi >= d0 + 31 ? 0u : (hi < d0 ? 0xffffffffu : ~((2u << (hi - d0)) - 1u));
+        return (raw & ~m_lo & ~m_hi) | (a1 & m_lo) | (fill_hi & m_hi);
+    };
+    if (nrec == 4) {   // D <= 64: the whole record is one 128-bit store
+        *reinterpret_cast<uint4*>(out) = make_uint4(a1, word(0), nw > 1 ? word(1) : 0u, nw > 2 ? word(2) : 0u);
+        return;
     }
+    out[0] = a1;
+    for (int w0 = 0; w0 < nw; w0++) out[1 + w0] = word(w0);
     for (int w0 = 1 + nw; w0 < nrec; w0++) out[w0] = 0u;
 }
 
@@ -188,7 +192,8 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
     unsigned char* ring = so_smem + (size_t)((wid * LPW + sub) * PF) * slot_bytes;
     const float* S = src + (size_t)pair * dm.vol_stride;
     float* O = dst + (size_t)pair * dm.vol_stride;
-    const unsigned* R = rec + (size_t)pair * dm.N * nrec;
+    const int variant = sx ? (sx > 0 ? 0 : 1) : (sy > 0 ? 2 : 3);
+    const unsigned* R = rec + ((size_t)pair * 4 + variant) * dm.N * nrec;
 
     const int x0 = sx ? (sx > 0 ? 0 : W - 1) : line;
     const int y0 = sy ? (sy > 0 ? 0 : dm.H - 1) : line;
@@ -311,13 +316,13 @@ static int launch_scanline_k(const AdcParams& P, const AdcWave& w, const float* 
 void adc_launch_so_bitrows(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
     dim3 grid(P.dm.H, w.S);
     k_so_bitrows<<<grid, 128, 0, st>>>(P.dm, P.tso, w.dmap, w.so_bitrows);
-    ++*launches;
+    dim3 rgrid((P.dm.N + 255) / 256, w.S, 4);
+    k_so_records<<<rgrid, 256, 0, st>>>(P.dm, P.tso, w.dmap, w.so_bitrows, w.so_rec);
+    *launches += 2;
 }
 
 int adc_launch_scanline(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
                         cudaStream_t st, unsigned long long* launches) {
-    dim3 grid((P.dm.N + 255) / 256, w.S);
-    k_so_records<<<grid, 256, 0, st>>>(P.dm, P.tso, sx, sy, w.dmap, w.so_bitrows, w.so_rec);
     // lanes per line: as few as keep K = ceil(Dp / lanes) <= 8 (Dp is a multiple of 4)
     const int Dp = P.dm.Dp;
     int rc = 1;
@@ -331,9 +336,9 @@ int adc_launch_scanline(const AdcParams& P, const AdcWave& w, const float* src, 
         switch ((Dp + 31) / 32) { case 5: SO_GO(5, 32); break; case 6: SO_GO(6, 32); break; case 7: SO_GO(7, 32); break; default: SO_GO(8, 32); }
     } else return 1;           // D > 256 not supported
 #undef SO_GO
-    *launches += 2;
+    ++*launches;
     return rc;
 }
 
-size_t adc_so_rec_bytes(const AdcDims& dm) { return (size_t)dm.N * so_rec_words(dm.Dp) * 4; }
+size_t adc_so_rec_bytes(const AdcDims& dm) { return (size_t)4 * dm.N * so_rec_words(dm.Dp) * 4; }   // four pass directions
 size_t adc_so_bitrow_bytes(const AdcDims& dm) { return (size_t)4 * dm.H * so_row_words(dm.W) * 4; }

@@ -460,7 +460,7 @@ bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st,
     const size_t smem = fixed + 2 * (size_t)slot_cap + ((size_t)slot_cap + 1) * 4;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_vote_push, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_vote_push, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);   // (+ static < 227 KB)
         attr_done = true;
     }
     k_vote_push<<<w.S, VP_THREADS, smem, st>>>(P, w.arms, w.vote_alr, w.vote_atbT, w.vote_pslotT, w.vote_state, hist,

@@ -147,14 +147,33 @@ k_wta_walk(AdcDims dm, int n_pairs, int seg_len, int n_seg, const float* __restr
 #pragma unroll
     for (int j = 0; j < NCH; j++) { rc[j] = ADC_LARGE_F; rb[j] = -1; }
     const int last_j = (D - 1) >> 5, last_lane = (D - 1) & 31;
-    for (int x = x_begin; x <= x_end; x++) {
+    // four columns per trip: their loads go out together (nothing of a later column's load depends on the chains),
+    // and the columns of the trip after that are pulled into L2 meanwhile
+    constexpr int UX = 4;
+    for (int xb = x_begin; xb <= x_end; xb += UX) {
+      float cc[UX][NCH];
+#pragma unroll
+      for (int u = 0; u < UX; u++) {
+          const int xx = xb + u;
+          const bool in2 = xx >= 0 && xx < W && xx <= x_end;
+#pragma unroll
+          for (int j = 0; j < NCH; j++) {
+              const int d = lane + 32 * j;
+              cc[u][j] = (in2 && d < D) ? __ldg(rowv + (size_t)xx * Dp + d) : ADC_INVALID_F;
+          }
+      }
+      {
+          const int xp = xb + 4 * UX + (lane >> 3);                 // 4 columns further on, 8 lanes (x 32 floats) per column
+          if (xp >= 0 && xp < W && (lane & 7) * 32 < Dp) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowv + (size_t)xp * Dp + (lane & 7) * 32));
+      }
+#pragma unroll
+      for (int u = 0; u < UX; u++) {
+        const int x = xb + u;
+        if (x > x_end) break;
         const bool inside = x >= 0 && x < W;
         float c[NCH];
 #pragma unroll
-        for (int j = 0; j < NCH; j++) {
-            const int d = lane + 32 * j;
-            c[j] = (inside && d < D) ? __ldg(rowv + (size_t)x * Dp + d) : ADC_INVALID_F;
-        }
+        for (int j = 0; j < NCH; j++) c[j] = cc[u][j];
         // ---- right view: shift the chains one lane up, then merge this column's candidates
         float carry_c = ADC_LARGE_F;   // enters lane 0 of chain 0: a fresh right pixel
         int carry_b = -1;
@@ -217,6 +236,7 @@ k_wta_walk(AdcDims dm, int n_pairs, int seg_len, int n_seg, const float* __restr
                 out_l[x] = o;
             }
         }
+      }
     }
 }
 
