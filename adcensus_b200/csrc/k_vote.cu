@@ -88,7 +88,7 @@ k_vote_slots(AdcDims dm, const int* __restrict__ vlist, const int* __restrict__ 
 __global__ void __launch_bounds__(VP_THREADS)
 k_vote_push(AdcParams P, const uchar4* __restrict__ arms_all, const uchar2* __restrict__ alr_all,
             const uchar2* __restrict__ atbT_all, const int* __restrict__ pslotT_all, const int* __restrict__ vstate_all,
-            unsigned* hist_all, long long hist_stride, int* cur_all, uint8_t* val_all, uint8_t* flag_all,
+            const uint16_t* __restrict__ sup_all, int* scratch_all, unsigned* hist_all, long long hist_stride, int* cur_all, uint8_t* val_all, uint8_t* flag_all,
             const int* __restrict__ vlist, int* counters, int* work_all, int2* chg_all,
             float* disp_old, float* disp_new, uint8_t* label, int cols_cap, int slot_cap, int force_enum) {
     extern __shared__ __align__(16) unsigned char vp_smem[];
@@ -103,6 +103,9 @@ k_vote_push(AdcParams P, const uchar4* __restrict__ arms_all, const uchar2* __re
     const uchar2* ATB = atbT_all + (size_t)pair * dm.N;
     const int* pslotT = pslotT_all + (size_t)pair * dm.N;
     const int* VS = vstate_all + (size_t)pair * dm.N;
+    const uint16_t* sup = sup_all + (size_t)pair * dm.N;
+    int* fbase = scratch_all + (size_t)pair * 2 * dm.N;   // [slot] start / length of a slot's forward list
+    int* fcnt = fbase + dm.N;
     unsigned* hist = hist_all + (size_t)pair * hist_stride;
     int* work = work_all + (size_t)pair * dm.N;
     int2* chg = chg_all + (size_t)pair * dm.N;
@@ -111,7 +114,6 @@ k_vote_push(AdcParams P, const uchar4* __restrict__ arms_all, const uchar2* __re
     uint8_t* lab = label + (size_t)pair * dm.N;
     int* cnt = counters + pair * ADC_CNT;
     const int n0 = __ldcg(cnt + 10), n1 = __ldcg(cnt + 11), ns = n0 + n1;
-    int* adj = reinterpret_cast<int*>(hist + (size_t)ns * HW);   // adjacency entries follow the histograms
     const int* list0 = vlist + ((size_t)pair * 2 + 0) * dm.N;
     const int* list1 = vlist + ((size_t)pair * 2 + 1) * dm.N;
     auto pix = [&](int s) { return s < n0 ? __ldg(list0 + s) : __ldg(list1 + (s - n0)); };
@@ -155,33 +157,88 @@ k_vote_push(AdcParams P, const uchar4* __restrict__ arms_all, const uchar2* __re
             ar[j] = (unsigned)v.x | ((unsigned)v.y << 8);
         }
         const int half = lane >> 4, sub = lane & 15;
-        for (int r0 = 0; r0 < rows; r0 += 2) {
-            const int ri = r0 + half;
-            unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
-            if (rows > 32) {
-                const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31), a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
-                a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
+        // eight rows per trip (two per half-warp pair x four), the first 32 columns of each fetched before any is
+        // consumed: 8 independent loads in flight per lane.  `visit` is called in warp-uniform control flow (it may use
+        // warp collectives); -1 (an invalid pixel that is nobody's slot) stands in for "no pixel here".
+        for (int r0 = 0; r0 < rows; r0 += 8) {
+            int v0[4], v1[4], cl[4], ch[4], ro[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int ri = r0 + 2 * t + half;
+                unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
+                if (rows > 32) {
+                    const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31), a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
+                    a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
+                }
+                ro[t] = rbase + ri * W;
+                cl[t] = -(int)(a2 & 255u) + sub;
+                ch[t] = ri < rows ? (int)(a2 >> 8) : -0x10000;     // rows past the region: empty segment
+                v0[t] = cl[t] <= ch[t] ? __ldg(VS + ro[t] + cl[t]) : -1;
+                v1[t] = cl[t] + 16 <= ch[t] ? __ldg(VS + ro[t] + cl[t] + 16) : -1;
             }
-            if (ri < rows) {
-                const int rowi = rbase + ri * W, c_hi = (int)(a2 >> 8);
-                for (int c = -(int)(a2 & 255u) + sub; c <= c_hi; c += 16) visit(__ldg(VS + rowi + c));
+#pragma unroll
+            for (int t = 0; t < 4; t++) { visit(v0[t]); visit(v1[t]); }
+            // rows wider than 32 pixels (rare): the remaining 16-column chunks, as many trips as the widest needs
+            int more = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) more = max(more, (ch[t] - cl[t]) / 16 - 1);
+            more = __reduce_max_sync(0xffffffffu, more);
+            for (int k = 2; k < 2 + more; k++) {
+#pragma unroll
+                for (int t = 0; t < 4; t++) visit(cl[t] + 16 * k <= ch[t] ? __ldg(VS + ro[t] + cl[t] + 16 * k) : -1);
             }
         }
     };
 
-    // ---- scan 1: histograms (packed two counters per word; a region holds < 65536 pixels) and list lengths
+    // ---- room for the forward lists?  (scan 1 writes, per slot, the pending pixels of its region; scan 2 then only has to
+    //      turn those lists around instead of walking the regions a second time).  A slot's list is at most its region:
+    //      sup[p] is that size (cross_aggregator.cpp:271-325; exact here because (2*L1+1)^2 < 65536).
+    if (tid == 0) { s_base = 0; s_fits = 1; s_nwork = 0; }
+    __syncthreads();
+    {
+        long long mine = 0;
+        for (int i = tid; i < ns; i += VP_THREADS) mine += (int)__ldg(sup + pix(i));
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (lane == 0) { s_warp[wid] = (int)min(mine, (long long)0x3fffffff); }
+        __syncthreads();
+        if (tid == 0) {
+            long long tot = 0;
+            for (int i = 0; i < VP_WARPS; i++) tot += s_warp[i];
+            s_base = (int)min(tot, (long long)0x3fffffff);
+        }
+        __syncthreads();
+    }
+    const long long fwd_words = s_base;
+    const bool use_fwd = !force_enum && (long long)ns * HW + fwd_words <= hist_stride;
+    int* fwd = reinterpret_cast<int*>(hist + (size_t)ns * HW);      // forward lists follow the histograms
+    int* adj = fwd + (use_fwd ? fwd_words : 0);                      // adjacency entries follow those
+    __syncthreads();
+    // ---- scan 1: histograms (packed two counters per word; a region holds < 65536 pixels), list lengths, forward lists
     for (int s = wid; s < ns; s += VP_WARPS) {
         for (int b = lane; b < D; b += 32) whist[b] = 0;
+        int fb = 0, fn = 0;
+        if (use_fwd) {
+            if (lane == 0) fb = atomicAdd(&s_nwork, (int)__ldg(sup + pix(s)));
+            fb = __shfl_sync(0xffffffffu, fb, 0);
+        }
         __syncwarp();
         scan_region(s, [&](int v) {
-            if (v >= 0) { if (v < D) atomicAdd(&whist[v], 1); }
-            else if (v < -1 && -v - 2 != s) atomicAdd(&cur[-v - 1], 1);   // length of t's list, kept at index t + 1
+            if (v >= 0 && v < D) atomicAdd(&whist[v], 1);
+            const bool edge = v < -1 && -v - 2 != s;
+            if (edge) atomicAdd(&cur[-v - 1], 1);                    // length of t's list, kept at index t + 1
+            if (use_fwd) {
+                const unsigned m = __ballot_sync(0xffffffffu, edge);
+                if (edge) fwd[fb + fn + __popc(m & ((1u << lane) - 1u))] = -v - 2;
+                fn += __popc(m);
+            }
         });
         __syncwarp();
         for (int w2 = lane; w2 < HW; w2 += 32) {
             const unsigned c0 = (unsigned)whist[2 * w2], c1 = (2 * w2 + 1 < D) ? (unsigned)whist[2 * w2 + 1] : 0u;
             hist[(size_t)s * HW + w2] = c0 | (c1 << 16);
         }
+        if (use_fwd && lane == 0) { fbase[s] = fb; fcnt[s] = fn; }
         __syncwarp();
     }
     __syncthreads();
@@ -215,13 +272,24 @@ k_vote_push(AdcParams P, const uchar4* __restrict__ arms_all, const uchar2* __re
         __syncthreads();
     }
     const int n_adj = s_base;
-    const bool use_adj = !force_enum && s_fits && (long long)ns * HW + n_adj <= hist_stride;
+    const bool use_adj = !force_enum && s_fits && (long long)ns * HW + (use_fwd ? fwd_words : 0) + n_adj <= hist_stride;
     // ---- scan 2: the lists themselves (afterwards cur[t] = end of t's list = start of t + 1's)
     if (use_adj) {
-        for (int s = wid; s < ns; s += VP_WARPS)
-            scan_region(s, [&](int v) {
-                if (v < -1 && -v - 2 != s) adj[atomicAdd(&cur[-v - 2], 1)] = s;
-            });
+        if (use_fwd) {
+            for (int s = wid; s < ns; s += VP_WARPS) {
+                const int fb = fbase[s], fn = fcnt[s];
+                for (int k = lane; k < fn; k += 64) {
+                    const int tA = fwd[fb + k], tB = k + 32 < fn ? fwd[fb + k + 32] : -1;
+                    adj[atomicAdd(&cur[tA], 1)] = s;
+                    if (tB >= 0) adj[atomicAdd(&cur[tB], 1)] = s;
+                }
+            }
+        } else {
+            for (int s = wid; s < ns; s += VP_WARPS)
+                scan_region(s, [&](int v) {
+                    if (v < -1 && -v - 2 != s) adj[atomicAdd(&cur[-v - 2], 1)] = s;
+                });
+        }
     }
     __syncthreads();
     if (tid == 0) { __stcg(cnt + 13, use_adj ? 1 : 0); __stcg(cnt + 14, n_adj); }
@@ -463,7 +531,8 @@ bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st,
         cudaFuncSetAttribute(k_vote_push, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);   // (+ static < 227 KB)
         attr_done = true;
     }
-    k_vote_push<<<w.S, VP_THREADS, smem, st>>>(P, w.arms, w.vote_alr, w.vote_atbT, w.vote_pslotT, w.vote_state, hist,
+    k_vote_push<<<w.S, VP_THREADS, smem, st>>>(P, w.arms, w.vote_alr, w.vote_atbT, w.vote_pslotT, w.vote_state, w.sup_h,
+                                              w.pend /* idle until the lists are rebuilt after voting */, hist,
                                               dm.vol_stride, w.vote_off, w.vote_val, w.vote_dirtyb, w.vlist, w.counters,
                                               w.last_eval, w.vote_dirty, w.disp_l, w.disp_t, w.label, cols_cap, slot_cap, force_enum);
     *launches += 3;

@@ -147,6 +147,8 @@ k_wta_walk(AdcDims dm, int n_pairs, int seg_len, int n_seg, const float* __restr
 #pragma unroll
     for (int j = 0; j < NCH; j++) { rc[j] = ADC_LARGE_F; rb[j] = -1; }
     const int last_j = (D - 1) >> 5, last_lane = (D - 1) & 31;
+    float pl_cost = ADC_LARGE_F, pr_cost = ADC_LARGE_F;   // parked results of this lane's column (left / right view)
+    int pl_best = 0, pr_best = -1;
     // four columns per trip: their loads go out together (nothing of a later column's load depends on the chains),
     // and the columns of the trip after that are pulled into L2 meanwhile
     constexpr int UX = 4;
@@ -186,26 +188,36 @@ k_wta_walk(AdcDims dm, int n_pairs, int seg_len, int n_seg, const float* __restr
             carry_c = tc; carry_b = tb;              // (only lane 0's copy is used: it received lane 31's pair)
             if (inside && lane + 32 * j < D && rc[j] > c[j]) { rc[j] = c[j]; rb[j] = lane + 32 * j; }   // strict '>'
         }
-        // the right pixel that just took its last candidate (d = D - 1)
-        {
+        // ---- results are parked in the lanes (lane = output column mod 32) and finished 32 at a time by the whole warp:
+        //      the parabola, its two neighbour loads and the store would otherwise run on a single lane every step
+        {   // the right pixel that just took its last candidate (d = D - 1)
             const int xr = x - dmin - (D - 1);
-            if (xr >= a && xr < b && lane == last_lane) {
+            if (xr >= a && xr < b) {
                 float rcl = rc[0];
                 int rbl = rb[0];
 #pragma unroll
                 for (int j = 1; j < NCH; j++) if (j == last_j) { rcl = rc[j]; rbl = rb[j]; }
-                // best starts at 0 (not dmin) when no column was valid, as in the reference (:271)
-                const int best = rbl >= 0 ? dmin + rbl : 0;
-                const float best_cost = rbl >= 0 ? rcl : ADC_LARGE_F;
-                float o = (float)best;
-                const int i1 = best - 1 - dmin, i2 = best + 1 - dmin;
-                if (best != dmin && best != dm.dmax - 1 && i1 >= 0 && i2 < D) {
-                    const int x1 = xr + best - 1, x2 = xr + best + 1;
-                    const float c1 = (x1 >= 0 && x1 < W) ? __ldg(rowv + (size_t)x1 * Dp + i1) : ADC_LARGE_F;   // (:277-286)
-                    const float c2 = (x2 >= 0 && x2 < W) ? __ldg(rowv + (size_t)x2 * Dp + i2) : ADC_LARGE_F;
-                    o = adc_subpixel(c1, c2, best_cost, best);
+                rcl = __shfl_sync(0xffffffffu, rcl, last_lane);
+                rbl = __shfl_sync(0xffffffffu, rbl, last_lane);
+                const int k = (xr - a) & 31;
+                if (lane == k) { pr_cost = rcl; pr_best = rbl; }
+                if (k == 31 || xr == b - 1) {
+                    const int xo = xr - k + lane;                     // this lane's right pixel
+                    if (lane <= k) {
+                        // best starts at 0 (not dmin) when no column was valid, as in the reference (:271)
+                        const int best = pr_best >= 0 ? dmin + pr_best : 0;
+                        const float best_cost = pr_best >= 0 ? pr_cost : ADC_LARGE_F;
+                        float o = (float)best;
+                        const int i1 = best - 1 - dmin, i2 = best + 1 - dmin;
+                        if (best != dmin && best != dm.dmax - 1 && i1 >= 0 && i2 < D) {
+                            const int x1 = xo + best - 1, x2 = xo + best + 1;
+                            const float c1 = (x1 >= 0 && x1 < W) ? __ldg(rowv + (size_t)x1 * Dp + i1) : ADC_LARGE_F;   // (:277-286)
+                            const float c2 = (x2 >= 0 && x2 < W) ? __ldg(rowv + (size_t)x2 * Dp + i2) : ADC_LARGE_F;
+                            o = adc_subpixel(c1, c2, best_cost, best);
+                        }
+                        out_r[xo] = o;
+                    }
                 }
-                out_r[xr] = o;
             }
         }
         // ---- left view of column x
@@ -226,14 +238,19 @@ k_wta_walk(AdcDims dm, int n_pairs, int seg_len, int n_seg, const float* __restr
                 best = dmin + di;
                 best_cost = __uint_as_float(m);
             }
-            if (lane == 0) {
-                float o = ADC_INVALID_F;
-                const int i1 = best - 1 - dmin, i2 = best + 1 - dmin;
-                if (best != dmin && best != dm.dmax - 1 && i1 >= 0 && i2 < D) {
-                    const float* v = rowv + (size_t)x * Dp;
-                    o = adc_subpixel(__ldg(v + i1), __ldg(v + i2), best_cost, best);
+            const int k = (x - a) & 31;
+            if (lane == k) { pl_cost = best_cost; pl_best = best; }
+            if (k == 31 || x == b - 1) {
+                const int xo = x - k + lane;
+                if (lane <= k) {
+                    float o = ADC_INVALID_F;
+                    const int i1 = pl_best - 1 - dmin, i2 = pl_best + 1 - dmin;
+                    if (pl_best != dmin && pl_best != dm.dmax - 1 && i1 >= 0 && i2 < D) {
+                        const float* v = rowv + (size_t)xo * Dp;
+                        o = adc_subpixel(__ldg(v + i1), __ldg(v + i2), pl_cost, pl_best);
+                    }
+                    out_l[xo] = o;
                 }
-                out_l[x] = o;
             }
         }
       }
