@@ -65,15 +65,128 @@ k_vote_transpose(AdcDims dm, const uchar4* __restrict__ arms, uchar2* __restrict
 // ---- slots.  slot = position in the active list (+ n0 for the occlusion list).  vstate[p]: rounded disparity
 // index of a valid pixel (254 = outside [0,D)), -1 = invalid, -(slot+2) = invalid and pending in slot. ----
 __global__ void __launch_bounds__(256)
-k_vote_slots(AdcDims dm, const int* __restrict__ vlist, const int* __restrict__ counters, int* __restrict__ vstate,
-             int* __restrict__ pslotT) {
+k_vote_slots(AdcDims dm, const int* __restrict__ vlist, int* __restrict__ counters, int* __restrict__ vstate,
+             int* __restrict__ pslotT, const uint16_t* __restrict__ sup) {
     const int pair = blockIdx.y;
     const int n0 = counters[pair * ADC_CNT + 10], n1 = counters[pair * ADC_CNT + 11];
+    unsigned room = 0;   // sum of the region sizes = upper bound of the forward lists (saturating)
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n0 + n1; s += gridDim.x * blockDim.x) {
         const int p = s < n0 ? vlist[((size_t)pair * 2 + 0) * dm.N + s] : vlist[((size_t)pair * 2 + 1) * dm.N + (s - n0)];
         const int y = p / dm.W, x = p - y * dm.W;
         vstate[(size_t)pair * dm.N + p] = -(s + 2);
         pslotT[(size_t)pair * dm.N + (size_t)x * dm.H + y] = s;
+        room += sup[(size_t)pair * dm.N + p];
+    }
+    room = __reduce_add_sync(0xffffffffu, min(room, 0x00ffffffu));
+    if ((threadIdx.x & 31) == 0 && room) {
+        const unsigned old = atomicAdd(reinterpret_cast<unsigned*>(counters + pair * ADC_CNT + 15), min(room, 0x1fffffffu));
+        if (old > 0x3fffffffu) atomicExch(reinterpret_cast<unsigned*>(counters + pair * ADC_CNT + 15), 0x7fffffffu);   // stays "too big"
+    }
+}
+
+// ---- region scan of one slot by one warp: eight rows per trip (two per half-warp pair x four), the first 32 columns of
+// each fetched before any is consumed (8 independent loads in flight per lane); the horizontal arms of all rows are
+// fetched up front (lane r holds rows r, r+32, r+64) and handed out by shuffle.  `visit` is called in warp-uniform
+// control flow (it may use warp collectives); -1 (an invalid pixel that is nobody's slot) stands in for "no pixel here".
+template <typename F>
+__device__ __forceinline__ void vote_scan_region(int p, int W, const uchar4* __restrict__ A, const uchar2* __restrict__ ALR,
+                                                 const int* __restrict__ VS, int lane, F&& visit) {
+    const int y = p / W, x = p - y * W;
+    const uchar4 a = __ldg(A + p);
+    const int top = a.z, rows = top + (int)a.w + 1;
+    const int rbase = (y - top) * W + x;
+    unsigned ar[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int ri = lane + 32 * j;
+        uchar2 v = make_uchar2(0, 0);
+        if (ri < rows) v = __ldg(ALR + rbase + ri * W);
+        ar[j] = (unsigned)v.x | ((unsigned)v.y << 8);
+    }
+    const int half = lane >> 4, sub = lane & 15;
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+        int v0[4], v1[4], cl[4], ch[4], ro[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int ri = r0 + 2 * t + half;
+            unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
+            if (rows > 32) {
+                const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31), a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
+                a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
+            }
+            ro[t] = rbase + ri * W;
+            cl[t] = -(int)(a2 & 255u) + sub;
+            ch[t] = ri < rows ? (int)(a2 >> 8) : -0x10000;     // rows past the region: empty segment
+            v0[t] = cl[t] <= ch[t] ? __ldg(VS + ro[t] + cl[t]) : -1;
+            v1[t] = cl[t] + 16 <= ch[t] ? __ldg(VS + ro[t] + cl[t] + 16) : -1;
+        }
+        int more = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) more = max(more, (ch[t] - cl[t]) / 16);
+        more = __reduce_max_sync(0xffffffffu, more);          // 16-column chunks the widest row of the trip needs, minus one
+#pragma unroll
+        for (int t = 0; t < 4; t++) visit(v0[t]);
+        if (more >= 1) {
+#pragma unroll
+            for (int t = 0; t < 4; t++) visit(v1[t]);
+        }
+        for (int k = 2; k <= more; k++) {                     // rows wider than 32 pixels (rare)
+#pragma unroll
+            for (int t = 0; t < 4; t++) visit(cl[t] + 16 * k <= ch[t] ? __ldg(VS + ro[t] + cl[t] + 16 * k) : -1);
+        }
+    }
+}
+
+// ---- batch-wide scan: histogram of every slot (D counters packed two per 32-bit word; a region holds < 65536 pixels) and,
+// when there is room, its forward list: the pending pixels (slots) of its region, written compacted at a base taken from
+// the pair's cursor (counters[9]).
+__global__ void __launch_bounds__(VI_WARPS * 32)
+k_vote_scan(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restrict__ alr_all, const int* __restrict__ vstate_all,
+            const uint16_t* __restrict__ sup_all, const int* __restrict__ vlist, int* counters, unsigned* __restrict__ hist_all,
+            long long hist_stride, int* __restrict__ scratch_all, int force_enum) {
+    __shared__ int s_hist[VI_WARPS][VP_MAXD];
+    const AdcDims& dm = P.dm;
+    const int pair = blockIdx.y;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int W = dm.W, D = dm.D, HW = (D + 1) >> 1;
+    int* cnt = counters + pair * ADC_CNT;
+    const int n0 = cnt[10], n1 = cnt[11], ns = n0 + n1;
+    const long long room = (unsigned)cnt[15];
+    const bool use_fwd = !force_enum && (long long)ns * HW + room <= hist_stride;
+    const uchar4* A = arms + (size_t)pair * dm.N;
+    const uchar2* ALR = alr_all + (size_t)pair * dm.N;
+    const int* VS = vstate_all + (size_t)pair * dm.N;
+    const uint16_t* sup = sup_all + (size_t)pair * dm.N;
+    unsigned* hist = hist_all + (size_t)pair * hist_stride;
+    int* fwd = reinterpret_cast<int*>(hist + (size_t)ns * HW);
+    int* fbase = scratch_all + (size_t)pair * 2 * dm.N;
+    int* fcnt = fbase + dm.N;
+    int* hs = s_hist[wid];
+    for (int s = blockIdx.x * VI_WARPS + wid; s < ns; s += gridDim.x * VI_WARPS) {
+        const int p = s < n0 ? vlist[((size_t)pair * 2 + 0) * dm.N + s] : vlist[((size_t)pair * 2 + 1) * dm.N + (s - n0)];
+        for (int b = lane; b < D; b += 32) hs[b] = 0;
+        int fb = 0, fn = 0;
+        if (use_fwd) {
+            if (lane == 0) fb = atomicAdd(cnt + 9, (int)sup[p]);
+            fb = __shfl_sync(0xffffffffu, fb, 0);
+        }
+        __syncwarp();
+        vote_scan_region(p, W, A, ALR, VS, lane, [&](int v) {
+            if (v >= 0 && v < D) atomicAdd(&hs[v], 1);
+            if (use_fwd) {
+                const bool edge = v < -1 && -v - 2 != s;
+                const unsigned m = __ballot_sync(0xffffffffu, edge);
+                if (edge) fwd[fb + fn + __popc(m & ((1u << lane) - 1u))] = -v - 2;
+                fn += __popc(m);
+            }
+        });
+        __syncwarp();
+        for (int w2 = lane; w2 < HW; w2 += 32) {
+            const unsigned c0 = (unsigned)hs[2 * w2], c1 = (2 * w2 + 1 < D) ? (unsigned)hs[2 * w2 + 1] : 0u;
+            hist[(size_t)s * HW + w2] = c0 | (c1 << 16);
+        }
+        if (use_fwd && lane == 0) { fbase[s] = fb; fcnt[s] = fn; }
+        __syncwarp();
     }
 }
 
@@ -86,9 +199,8 @@ k_vote_slots(AdcDims dm, const int* __restrict__ vlist, const int* __restrict__ 
 #define VP_FLAG_DEAD 2
 
 __global__ void __launch_bounds__(VP_THREADS)
-k_vote_push(AdcParams P, const uchar4* __restrict__ arms_all, const uchar2* __restrict__ alr_all,
-            const uchar2* __restrict__ atbT_all, const int* __restrict__ pslotT_all, const int* __restrict__ vstate_all,
-            const uint16_t* __restrict__ sup_all, int* scratch_all, unsigned* hist_all, long long hist_stride, int* cur_all, uint8_t* val_all, uint8_t* flag_all,
+k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
+            const uchar2* __restrict__ atbT_all, const int* __restrict__ pslotT_all, const int* scratch_all, unsigned* hist_all, long long hist_stride, int* cur_all, uint8_t* val_all, uint8_t* flag_all,
             const int* __restrict__ vlist, int* counters, int* work_all, int2* chg_all,
             float* disp_old, float* disp_new, uint8_t* label, int cols_cap, int slot_cap, int force_enum) {
     extern __shared__ __align__(16) unsigned char vp_smem[];
@@ -98,14 +210,11 @@ k_vote_push(AdcParams P, const uchar4* __restrict__ arms_all, const uchar2* __re
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int W = dm.W, H = dm.H, D = dm.D, HW = (D + 1) >> 1;
     const int L1 = max(P.L1, 0), R = 2 * L1 + 1;
-    const uchar4* A = arms_all + (size_t)pair * dm.N;
     const uchar2* ALR = alr_all + (size_t)pair * dm.N;
     const uchar2* ATB = atbT_all + (size_t)pair * dm.N;
     const int* pslotT = pslotT_all + (size_t)pair * dm.N;
-    const int* VS = vstate_all + (size_t)pair * dm.N;
-    const uint16_t* sup = sup_all + (size_t)pair * dm.N;
-    int* fbase = scratch_all + (size_t)pair * 2 * dm.N;   // [slot] start / length of a slot's forward list
-    int* fcnt = fbase + dm.N;
+    const int* fbase = scratch_all + (size_t)pair * 2 * dm.N;   // [slot] start / length of a slot's forward list
+    const int* fcnt = fbase + dm.N;
     unsigned* hist = hist_all + (size_t)pair * hist_stride;
     int* work = work_all + (size_t)pair * dm.N;
     int2* chg = chg_all + (size_t)pair * dm.N;
@@ -117,11 +226,9 @@ k_vote_push(AdcParams P, const uchar4* __restrict__ arms_all, const uchar2* __re
     const int* list0 = vlist + ((size_t)pair * 2 + 0) * dm.N;
     const int* list1 = vlist + ((size_t)pair * 2 + 1) * dm.N;
     auto pix = [&](int s) { return s < n0 ? __ldg(list0 + s) : __ldg(list1 + (s - n0)); };
-    // shared memory: [fallback column lists][per-warp histogram of the first scan][val][flg][cur]
+    // shared memory: [fallback column lists][val][flg][cur]
     unsigned short* cols = reinterpret_cast<unsigned short*>(vp_smem) + (size_t)wid * cols_cap;
-    const int hist_cap = (D + 31) & ~31;
-    int* whist = reinterpret_cast<int*>(vp_smem + (size_t)VP_WARPS * cols_cap * 2) + (size_t)wid * hist_cap;
-    unsigned char* after_hist = vp_smem + (size_t)VP_WARPS * cols_cap * 2 + (size_t)VP_WARPS * hist_cap * 4;
+    unsigned char* after_hist = vp_smem + (size_t)VP_WARPS * cols_cap * 2;
     uint8_t* val;    // [slot] current vote, 255 = none
     uint8_t* flg;    // [slot] VP_FLAG_*
     int* cur;        // [slot + 1] list lengths -> list starts -> fill cursors (= list ends once filled)
@@ -140,106 +247,22 @@ k_vote_push(AdcParams P, const uchar4* __restrict__ arms_all, const uchar2* __re
     __syncthreads();
     int rounds_total = 0, derives = 0, changes = 0;
 
-    // ---- region scan of slot s by one warp: two region rows per trip (one per half-warp), 16 columns per step; the
-    //      horizontal arms of all rows are fetched up front (lane r holds rows r, r+32, r+64) and handed out by shuffle
-    auto scan_region = [&](int s, auto&& visit) {
-        const int p = pix(s);
-        const int y = p / W, x = p - y * W;
-        const uchar4 a = __ldg(A + p);
-        const int top = a.z, rows = top + (int)a.w + 1;
-        const int rbase = (y - top) * W + x;
-        unsigned ar[3];
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            const int ri = lane + 32 * j;
-            uchar2 v = make_uchar2(0, 0);
-            if (ri < rows) v = __ldg(ALR + rbase + ri * W);
-            ar[j] = (unsigned)v.x | ((unsigned)v.y << 8);
-        }
-        const int half = lane >> 4, sub = lane & 15;
-        // eight rows per trip (two per half-warp pair x four), the first 32 columns of each fetched before any is
-        // consumed: 8 independent loads in flight per lane.  `visit` is called in warp-uniform control flow (it may use
-        // warp collectives); -1 (an invalid pixel that is nobody's slot) stands in for "no pixel here".
-        for (int r0 = 0; r0 < rows; r0 += 8) {
-            int v0[4], v1[4], cl[4], ch[4], ro[4];
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const int ri = r0 + 2 * t + half;
-                unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
-                if (rows > 32) {
-                    const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31), a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
-                    a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
-                }
-                ro[t] = rbase + ri * W;
-                cl[t] = -(int)(a2 & 255u) + sub;
-                ch[t] = ri < rows ? (int)(a2 >> 8) : -0x10000;     // rows past the region: empty segment
-                v0[t] = cl[t] <= ch[t] ? __ldg(VS + ro[t] + cl[t]) : -1;
-                v1[t] = cl[t] + 16 <= ch[t] ? __ldg(VS + ro[t] + cl[t] + 16) : -1;
-            }
-#pragma unroll
-            for (int t = 0; t < 4; t++) { visit(v0[t]); visit(v1[t]); }
-            // rows wider than 32 pixels (rare): the remaining 16-column chunks, as many trips as the widest needs
-            int more = 0;
-#pragma unroll
-            for (int t = 0; t < 4; t++) more = max(more, (ch[t] - cl[t]) / 16 - 1);
-            more = __reduce_max_sync(0xffffffffu, more);
-            for (int k = 2; k < 2 + more; k++) {
-#pragma unroll
-                for (int t = 0; t < 4; t++) visit(cl[t] + 16 * k <= ch[t] ? __ldg(VS + ro[t] + cl[t] + 16 * k) : -1);
+    // ---- adjacency lists (CSR by target) from the forward lists of k_vote_scan: count, prefix, fill
+    const long long room = (unsigned)__ldcg(cnt + 15);
+    const bool use_fwd = !force_enum && (long long)ns * HW + room <= hist_stride;
+    const int* fwd = reinterpret_cast<const int*>(hist + (size_t)ns * HW);
+    int* adj = reinterpret_cast<int*>(hist + (size_t)ns * HW) + (use_fwd ? room : 0);
+    unsigned long long t_start = 0;
+    if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    if (use_fwd) {
+        for (int s = wid; s < ns; s += VP_WARPS) {
+            const int fb = fbase[s], fn = fcnt[s];
+            for (int k = lane; k < fn; k += 64) {
+                const int tA = __ldg(fwd + fb + k), tB = k + 32 < fn ? __ldg(fwd + fb + k + 32) : -1;
+                atomicAdd(&cur[tA + 1], 1);                          // length of t's list, kept at index t + 1
+                if (tB >= 0) atomicAdd(&cur[tB + 1], 1);
             }
         }
-    };
-
-    // ---- room for the forward lists?  (scan 1 writes, per slot, the pending pixels of its region; scan 2 then only has to
-    //      turn those lists around instead of walking the regions a second time).  A slot's list is at most its region:
-    //      sup[p] is that size (cross_aggregator.cpp:271-325; exact here because (2*L1+1)^2 < 65536).
-    if (tid == 0) { s_base = 0; s_fits = 1; s_nwork = 0; }
-    __syncthreads();
-    {
-        long long mine = 0;
-        for (int i = tid; i < ns; i += VP_THREADS) mine += (int)__ldg(sup + pix(i));
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-        if (lane == 0) { s_warp[wid] = (int)min(mine, (long long)0x3fffffff); }
-        __syncthreads();
-        if (tid == 0) {
-            long long tot = 0;
-            for (int i = 0; i < VP_WARPS; i++) tot += s_warp[i];
-            s_base = (int)min(tot, (long long)0x3fffffff);
-        }
-        __syncthreads();
-    }
-    const long long fwd_words = s_base;
-    const bool use_fwd = !force_enum && (long long)ns * HW + fwd_words <= hist_stride;
-    int* fwd = reinterpret_cast<int*>(hist + (size_t)ns * HW);      // forward lists follow the histograms
-    int* adj = fwd + (use_fwd ? fwd_words : 0);                      // adjacency entries follow those
-    __syncthreads();
-    // ---- scan 1: histograms (packed two counters per word; a region holds < 65536 pixels), list lengths, forward lists
-    for (int s = wid; s < ns; s += VP_WARPS) {
-        for (int b = lane; b < D; b += 32) whist[b] = 0;
-        int fb = 0, fn = 0;
-        if (use_fwd) {
-            if (lane == 0) fb = atomicAdd(&s_nwork, (int)__ldg(sup + pix(s)));
-            fb = __shfl_sync(0xffffffffu, fb, 0);
-        }
-        __syncwarp();
-        scan_region(s, [&](int v) {
-            if (v >= 0 && v < D) atomicAdd(&whist[v], 1);
-            const bool edge = v < -1 && -v - 2 != s;
-            if (edge) atomicAdd(&cur[-v - 1], 1);                    // length of t's list, kept at index t + 1
-            if (use_fwd) {
-                const unsigned m = __ballot_sync(0xffffffffu, edge);
-                if (edge) fwd[fb + fn + __popc(m & ((1u << lane) - 1u))] = -v - 2;
-                fn += __popc(m);
-            }
-        });
-        __syncwarp();
-        for (int w2 = lane; w2 < HW; w2 += 32) {
-            const unsigned c0 = (unsigned)whist[2 * w2], c1 = (2 * w2 + 1 < D) ? (unsigned)whist[2 * w2 + 1] : 0u;
-            hist[(size_t)s * HW + w2] = c0 | (c1 << 16);
-        }
-        if (use_fwd && lane == 0) { fbase[s] = fb; fcnt[s] = fn; }
-        __syncwarp();
     }
     __syncthreads();
     // ---- inclusive prefix sum over cur[0..ns]: cur[t] = start of t's list, cur[ns] = number of entries
@@ -272,27 +295,24 @@ k_vote_push(AdcParams P, const uchar4* __restrict__ arms_all, const uchar2* __re
         __syncthreads();
     }
     const int n_adj = s_base;
-    const bool use_adj = !force_enum && s_fits && (long long)ns * HW + (use_fwd ? fwd_words : 0) + n_adj <= hist_stride;
-    // ---- scan 2: the lists themselves (afterwards cur[t] = end of t's list = start of t + 1's)
+    const bool use_adj = use_fwd && s_fits && (long long)ns * HW + room + n_adj <= hist_stride;
+    // ---- fill (afterwards cur[t] = end of t's list = start of t + 1's)
     if (use_adj) {
-        if (use_fwd) {
-            for (int s = wid; s < ns; s += VP_WARPS) {
-                const int fb = fbase[s], fn = fcnt[s];
-                for (int k = lane; k < fn; k += 64) {
-                    const int tA = fwd[fb + k], tB = k + 32 < fn ? fwd[fb + k + 32] : -1;
-                    adj[atomicAdd(&cur[tA], 1)] = s;
-                    if (tB >= 0) adj[atomicAdd(&cur[tB], 1)] = s;
-                }
+        for (int s = wid; s < ns; s += VP_WARPS) {
+            const int fb = fbase[s], fn = fcnt[s];
+            for (int k = lane; k < fn; k += 64) {
+                const int tA = __ldg(fwd + fb + k), tB = k + 32 < fn ? __ldg(fwd + fb + k + 32) : -1;
+                adj[atomicAdd(&cur[tA], 1)] = s;
+                if (tB >= 0) adj[atomicAdd(&cur[tB], 1)] = s;
             }
-        } else {
-            for (int s = wid; s < ns; s += VP_WARPS)
-                scan_region(s, [&](int v) {
-                    if (v < -1 && -v - 2 != s) adj[atomicAdd(&cur[-v - 2], 1)] = s;
-                });
         }
     }
     __syncthreads();
-    if (tid == 0) { __stcg(cnt + 13, use_adj ? 1 : 0); __stcg(cnt + 14, n_adj); }
+    if (tid == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        __stcg(cnt + 13, use_adj ? 1 : 0); __stcg(cnt + 14, n_adj); __stcg(cnt + 4, (int)((t1 - t_start) / 1000));   // us spent building the lists
+    }
 
     // value change of the pixel in slot t (a -> b, 255 = invalid) -> histograms of the pending pixels whose region
     // holds it.
@@ -515,11 +535,17 @@ bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st,
     dim3 tgrid((dm.W + 31) / 32, (dm.H + 31) / 32, w.S);
     k_vote_transpose<<<tgrid, 256, 0, st>>>(dm, w.arms, w.vote_atbT);
     dim3 sgrid(64, w.S);
-    k_vote_slots<<<sgrid, 256, 0, st>>>(dm, w.vlist, w.counters, w.vote_state, w.vote_pslotT);
+    k_vote_slots<<<sgrid, 256, 0, st>>>(dm, w.vlist, w.counters, w.vote_state, w.vote_pslotT, w.sup_h);
     unsigned* hist = reinterpret_cast<unsigned*>(w.volB);
+    int gx = (148 * 8 + w.S - 1) / w.S;
+    if (gx < 1) gx = 1;
+    dim3 igrid(gx, w.S);
+    k_vote_scan<<<igrid, VI_WARPS * 32, 0, st>>>(P, w.arms, w.vote_alr, w.vote_state, w.sup_h, w.vlist, w.counters, hist,
+                                                 dm.vol_stride, w.pend /* idle until the lists are rebuilt after voting */,
+                                                 force_enum);
     const int cols_cap = (2 * L1 + 1 + 7) / 8 * 8;
-    // shared memory: column lists (fallback), one histogram per warp, then val / flg / cur for as many slots as fit
-    const size_t fixed = (size_t)VP_WARPS * cols_cap * 2 + (size_t)VP_WARPS * ((dm.D + 31) & ~31) * 4;
+    // shared memory: column lists (fallback), then val / flg / cur for as many slots as fit
+    const size_t fixed = (size_t)VP_WARPS * cols_cap * 2;
     int slot_cap = (int)((220 * 1024 - fixed - 16) / 6) & ~15;
     if (slot_cap > VP_SMEM_SLOTS) slot_cap = VP_SMEM_SLOTS;
     static int cap_override = -1;   // ADC_VOTE_SLOTCAP: shrink the shared-memory slot capacity (tests of the global-memory state)
@@ -531,10 +557,9 @@ bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st,
         cudaFuncSetAttribute(k_vote_push, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);   // (+ static < 227 KB)
         attr_done = true;
     }
-    k_vote_push<<<w.S, VP_THREADS, smem, st>>>(P, w.arms, w.vote_alr, w.vote_atbT, w.vote_pslotT, w.vote_state, w.sup_h,
-                                              w.pend /* idle until the lists are rebuilt after voting */, hist,
-                                              dm.vol_stride, w.vote_off, w.vote_val, w.vote_dirtyb, w.vlist, w.counters,
-                                              w.last_eval, w.vote_dirty, w.disp_l, w.disp_t, w.label, cols_cap, slot_cap, force_enum);
-    *launches += 3;
+    k_vote_push<<<w.S, VP_THREADS, smem, st>>>(P, w.vote_alr, w.vote_atbT, w.vote_pslotT, w.pend, hist, dm.vol_stride,
+                                              w.vote_off, w.vote_val, w.vote_dirtyb, w.vlist, w.counters, w.last_eval,
+                                              w.vote_dirty, w.disp_l, w.disp_t, w.label, cols_cap, slot_cap, force_enum);
+    *launches += 4;
     return true;
 }

@@ -250,7 +250,8 @@ def test_voting_fallback_paths(tmp_path, env):
             eng = A.Engine(w, h, A.ADCensusOption(max_disparity=D))
             orc.begin(left, right); orc.run_to("VOTE")
             eng.debug_run(left, right, "VOTE")
-            assert eng.counters()[13] == (0 if %r else 1), "wrong adjacency / enumeration path"
+            c = eng.counters()
+            assert c[13] == (0 if %r else 1), f"wrong adjacency / enumeration path: counters {c} for {w}x{h}x{D}"
             for tap in ("DISP_L", "MISMATCHES", "OCCLUSIONS"):
                 g, o = eng.tap(tap), orc.tap(tap)
                 assert g.shape == o.shape and g.tobytes() == o.tobytes(), tap
