@@ -468,9 +468,10 @@ int adc_create(int32_t width, int32_t height, const adc_option* opt, const adc_c
     auto bail = [&](int rc) { adc_destroy(e); return rc; };
     if (cudaSetDevice(e->cfg.device) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "cudaSetDevice failed"));
 
-    // wave size: enough scanlines in flight for the warp-per-line scanline kernels (~6k lines = 40 warps/SM)
+    // wave size: enough scanlines in flight for the line-per-lane-group scanline kernels (measured on Cone: 32 pairs
+    // per wave x 4 lanes beats 16 x 6; the scanline passes only have W or H lines per pair to spread over 148 SMs)
     int S = e->cfg.wave_pairs;
-    if (S <= 0) S = std::min(32, std::max(2, (6144 + std::min(width, height) - 1) / std::min(width, height)));
+    if (S <= 0) S = std::min(32, std::max(2, (12288 + std::min(width, height) - 1) / std::min(width, height)));
     int nl = e->cfg.lanes > 0 ? e->cfg.lanes : 4;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "cudaMemGetInfo failed"));

@@ -110,7 +110,8 @@ k_wta_right_finish(AdcDims dm, const float* __restrict__ vol, const unsigned lon
 }
 
 // ---------------------------------------------------------------------------------------------
-// Row-walking kernel (default for D <= 256).  k_wta_tile below turned out to be bound by instruction issue
+// Row-walking kernel (experimental, ADC_WTA_MODE=1; 490 us per wave of 16 Cone pairs against 312 us of the tile kernel,
+// both issue-bound).  k_wta_tile below turned out to be bound by instruction issue
 // (one thread per pixel scanning its D costs one by one out of shared memory, ~1400 thread instructions per
 // pixel for the two views).  Here a warp walks along an image row, lane = disparity:
 //   left view : the pixel's D costs sit in the lanes (d = lane + 32 j); non-negative floats order like their
@@ -277,7 +278,7 @@ static void launch_wta_walk(const AdcParams& P, const AdcWave& w, const float* v
 // the reference's strict '>' comparison.  The halo columns are read twice (second time from L2).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_wta_tile(AdcDims dm, int wpx, const float* __restrict__ vol, float* __restrict__ disp_l, float* __restrict__ disp_r) {
+k_wta_tile(AdcDims dm, int wpx, int3 pf, const float* __restrict__ vol, float* __restrict__ disp_l, float* __restrict__ disp_r) {
     extern __shared__ float wt_tile[];
     const int pair = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * wpx;
     const int Q = dm.Dp >> 2, DS = dm.Dp + 1;
@@ -285,11 +286,12 @@ k_wta_tile(AdcDims dm, int wpx, const float* __restrict__ vol, float* __restrict
     const int col_hi = x0 + wpx - 1 + max(0, dm.dmax - 1);
     const int ncols = col_hi - col_lo + 1;
     const float* rowv = vol + (size_t)pair * dm.vol_stride + (size_t)y * dm.W * dm.Dp;
-    {   // warm L2 with the core columns of the CTA that runs ~one wave of CTAs later in launch order
-        long long lin = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + 148 * 4;
-        if (lin < (long long)gridDim.x * gridDim.y * gridDim.z) {
-            const int bx2 = (int)(lin % gridDim.x); lin /= gridDim.x;
-            const int by2 = (int)(lin % gridDim.y); const int bz2 = (int)(lin / gridDim.y);
+    {   // warm L2 with the core columns of the CTA that runs ~one wave of CTAs later in launch order (pf = that
+        // displacement decomposed into block coordinates by the host: three carries instead of 64-bit divisions)
+        int bx2 = blockIdx.x + pf.x, by2 = blockIdx.y + pf.y, bz2 = blockIdx.z + pf.z;
+        if (bx2 >= (int)gridDim.x) { bx2 -= gridDim.x; by2++; }
+        if (by2 >= (int)gridDim.y) { by2 -= gridDim.y; bz2++; }
+        if (pf.x >= 0 && bz2 < (int)gridDim.z) {
             const float* r2 = vol + (size_t)bz2 * dm.vol_stride + ((size_t)by2 * dm.W + (size_t)bx2 * wpx) * dm.Dp;
             const int lines = min(wpx, dm.W - bx2 * wpx) * dm.Dp / 32;      // 128-byte lines of the core tile
             for (int i = threadIdx.x; i < lines; i += blockDim.x) asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + (size_t)i * 32));
@@ -350,8 +352,8 @@ k_wta_tile(AdcDims dm, int wpx, const float* __restrict__ vol, float* __restrict
 }
 
 int adc_launch_wta(const AdcParams& P, const AdcWave& w, const float* vol, cudaStream_t st, unsigned long long* launches) {
-    static int mode = -1;   // development switch ADC_WTA_MODE: 1 = row-walking kernel (default), 0 = tile / atomic kernels
-    if (mode < 0) { const char* m = getenv("ADC_WTA_MODE"); mode = m ? atoi(m) : 1; }
+    static int mode = -1;   // development switch ADC_WTA_MODE: 0 = tile / atomic kernels (default), 1 = row-walking kernel (measured slower so far)
+    if (mode < 0) { const char* m = getenv("ADC_WTA_MODE"); mode = m ? atoi(m) : 0; }
     if (mode == 1 && P.dm.D <= 256) {
         switch ((P.dm.D + 31) / 32) {
             case 1: launch_wta_walk<1>(P, w, vol, st); break;
@@ -377,7 +379,9 @@ int adc_launch_wta(const AdcParams& P, const AdcWave& w, const float* vol, cudaS
             attr_done = true;
         }
         dim3 grid((P.dm.W + wpx - 1) / wpx, P.dm.H, w.S);
-        k_wta_tile<<<grid, 2 * wpx, tile_bytes, st>>>(P.dm, wpx, vol, w.disp_l, w.disp_r);
+        const long long pfd = 148 * 4;
+        const int3 pf = make_int3((int)(pfd % grid.x), (int)((pfd / grid.x) % grid.y), (int)(pfd / grid.x / grid.y));
+        k_wta_tile<<<grid, 2 * wpx, tile_bytes, st>>>(P.dm, wpx, pf, vol, w.disp_l, w.disp_r);
         ++*launches;
         return 0;
     }

@@ -250,8 +250,10 @@ def test_voting_fallback_paths(tmp_path, env):
             eng = A.Engine(w, h, A.ADCensusOption(max_disparity=D))
             orc.begin(left, right); orc.run_to("VOTE")
             eng.debug_run(left, right, "VOTE")
-            c = eng.counters()
-            assert c[13] == (0 if %r else 1), f"wrong adjacency / enumeration path: counters {c} for {w}x{h}x{D}"
+            c = eng.counters()   # [13] = 1 when the adjacency lists were used (they need room in the idle cost volume,
+            #                      which small images with long lists do not have -- Cone does)
+            if %r: assert c[13] == 0, f"adjacency lists used although ADC_VOTE_ENUM=1: counters {c}"
+            elif (w, h) == (450, 375): assert c[13] == 1, f"Cone fell back to enumeration: counters {c}"
             for tap in ("DISP_L", "MISMATCHES", "OCCLUSIONS"):
                 g, o = eng.tap(tap), orc.tap(tap)
                 assert g.shape == o.shape and g.tobytes() == o.tobytes(), tap
