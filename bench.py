@@ -257,13 +257,18 @@ def run_gpu_arm(args):
         share = {"arm_sum": 4 * (kern["arm_sum_h"]["ms_per_launch"] + kern["arm_sum_v_div"]["ms_per_launch"]),
                  "scanline": 2 * (kern["scanline_x"]["ms_per_launch"] + kern["scanline_y"]["ms_per_launch"])}
         dom = "scanline_x" if share["scanline"] >= share["arm_sum"] else "arm_sum_v_div"
+        # measured DRAM bytes of that kernel (ncu --set full capture summarised in profiles/; per pair there, per launch here)
         traffic = None
         tf = ROOT / "profiles" / "traffic.json"
         if tf.exists():
-            traffic = json.loads(tf.read_text()).get(dom)
+            per_pair = json.loads(tf.read_text()).get(dom, {}).get("dram_bytes_per_pair")
+            if per_pair:
+                traffic = round(per_pair * eng.wave_pairs)
         roof = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": kern[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                "note": "algorithmic bytes per launch = (2V + 6N) per pair x pairs per launch, V = 4*H*W*D (SURVEY 8d)"}
+                "note": "algorithmic bytes per launch = (2V + 6N) per pair x pairs per launch, V = 4*H*W*D (SURVEY 8d); "
+                        "traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture "
+                        "(profiles/r1_ncu_full_v26_summary.csv); kernel timed alone with CUDA events on the engine's stream"}
         total_maps = world * n * args.steps
         value = total_maps / (ms_dev * 1e-3)
         e2e_v = total_maps / (ms_e2e * 1e-3)
