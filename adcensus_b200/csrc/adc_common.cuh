@@ -120,5 +120,10 @@ bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st,
 void adc_launch_interp_list(const AdcParams& P, const AdcWave& w, int k, cudaStream_t st, unsigned long long* launches);
 void adc_launch_discontinuity(const AdcParams& P, const AdcWave& w, const float* vol, cudaStream_t st, unsigned long long* launches);
 // in-place-equivalent 3x3 median: reads `in`, writes `out` (different buffers); non-zero if H is too large
+// output side of the demo (k_render.cu): 8-bit normalised map + JET colouring; (x,y,d,r,g,b) cloud of the valid pixels
+int adc_launch_render(const AdcDims& dm, const float* d_disp, unsigned* d_mm, uint8_t* d_gray, uint8_t* d_jet, float* d_mm_out,
+                      cudaStream_t st, unsigned long long* launches);
+void adc_launch_cloud(const AdcParams& P, const AdcWave& w1, const float* d_disp, const uint8_t* d_bgr, float* d_cloud,
+                      cudaStream_t st, unsigned long long* launches);
 int adc_launch_median(const AdcParams& P, const AdcWave& w, const float* in, float* out, cudaStream_t st,
                       unsigned long long* launches);

@@ -609,6 +609,57 @@ int adc_get_config(const adc_engine* e, adc_config* out) {
     return ADC_OK;
 }
 
+// ---- output side of the reference's demo (main.cpp:147-230), SURVEY.md 8(f) rank 3 ----------------------------
+int adc_render_disparity(adc_engine* e, const float* disp, uint8_t* gray8, uint8_t* jet_bgr, float* min_max) {
+    if (!e) return fail(ADC_ERR_ARG, "adc_render_disparity: engine is NULL");
+    if (!disp || (!gray8 && !jet_bgr && !min_max)) return fail(ADC_ERR_ARG, "adc_render_disparity: NULL map or no output requested");
+    CK(cudaSetDevice(e->cfg.device));
+    Lane& ln = e->lanes[0];
+    int rc = drain_lane(e, ln);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ln.st));
+    const size_t N = (size_t)e->P.dm.N;
+    // lane 0's buffers are idle between calls: disp_t holds the map, flag the 8-bit image, bgr the colour image,
+    // the first words of tile_stamp the min/max keys and (as floats) the values handed back
+    float* d_disp = ln.w.disp_t;
+    unsigned* d_mm = reinterpret_cast<unsigned*>(ln.w.rowcnt);
+    float* d_mm_out = reinterpret_cast<float*>(ln.w.rowcnt) + 2;
+    CK(cudaMemcpyAsync(d_disp, disp, N * sizeof(float), cudaMemcpyHostToDevice, ln.st));
+    if (adc_launch_render(e->P.dm, d_disp, d_mm, ln.w.flag, ln.w.bgr, d_mm_out, ln.st, &e->launches))
+        return fail(ADC_ERR_CUDA, "adc_render_disparity: colour table upload failed");
+    if (gray8) CK(cudaMemcpyAsync(gray8, ln.w.flag, N, cudaMemcpyDeviceToHost, ln.st));
+    if (jet_bgr) CK(cudaMemcpyAsync(jet_bgr, ln.w.bgr, 3 * N, cudaMemcpyDeviceToHost, ln.st));
+    if (min_max) CK(cudaMemcpyAsync(min_max, d_mm_out, 2 * sizeof(float), cudaMemcpyDeviceToHost, ln.st));
+    CK(cudaStreamSynchronize(ln.st));
+    CK(cudaGetLastError());
+    return ADC_OK;
+}
+
+int adc_disparity_cloud(adc_engine* e, const uint8_t* img_left, const float* disp, float* cloud, int32_t* n_points) {
+    if (!e) return fail(ADC_ERR_ARG, "adc_disparity_cloud: engine is NULL");
+    if (!img_left || !disp || !cloud || !n_points) return fail(ADC_ERR_ARG, "adc_disparity_cloud: NULL pointer");
+    CK(cudaSetDevice(e->cfg.device));
+    Lane& ln = e->lanes[0];
+    int rc = drain_lane(e, ln);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ln.st));
+    const size_t N = (size_t)e->P.dm.N;
+    const AdcWave w1 = wave_view(e, ln, 1);
+    float* d_cloud = ln.w.volA;                       // 6 floats per pixel at most; a volume has Dp >= 4 ... use both volumes' span
+    if ((size_t)e->P.dm.vol_stride * 2 < N * 6) return fail(ADC_ERR_UNSUPPORTED, "adc_disparity_cloud: disparity range too small for the scratch volume");
+    CK(cudaMemcpyAsync(ln.w.disp_t, disp, N * sizeof(float), cudaMemcpyHostToDevice, ln.st));
+    CK(cudaMemcpyAsync(ln.w.bgr, img_left, 3 * N, cudaMemcpyHostToDevice, ln.st));
+    CK(cudaMemsetAsync(ln.w.counters, 0, ADC_CNT * sizeof(int), ln.st));
+    adc_launch_cloud(e->P, w1, ln.w.disp_t, ln.w.bgr, d_cloud, ln.st, &e->launches);
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, ln.w.counters, sizeof(int), cudaMemcpyDeviceToHost, ln.st));
+    CK(cudaStreamSynchronize(ln.st));
+    if (n > 0) CK(cudaMemcpy(cloud, d_cloud, (size_t)n * 6 * sizeof(float), cudaMemcpyDeviceToHost));
+    *n_points = n;
+    CK(cudaGetLastError());
+    return ADC_OK;
+}
+
 // ---- per-kernel timing for the roofline figures of bench.py ------------------------------------
 // Re-launches ONE kernel of the pipeline `reps` times on lane 0's wave buffers (which hold whatever
 // the last batch left there; every kernel below is data-oblivious in its memory traffic except for

@@ -93,6 +93,8 @@ def load_library() -> ctypes.CDLL:
     L.adc_last_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 6)]
     L.adc_get_config.argtypes = [vp, ctypes.POINTER(_Config)]
     L.adc_profile_kernel.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]
+    L.adc_render_disparity.argtypes = [vp, f32p, u8p, u8p, f32p]
+    L.adc_disparity_cloud.argtypes = [vp, u8p, f32p, f32p, ctypes.POINTER(ctypes.c_int32)]
     L.adc_last_error.restype = ctypes.c_char_p
     L.adc_version.restype = ctypes.c_char_p
     L.adc_debug_run.argtypes = [vp, u8p, u8p, i32]
@@ -199,6 +201,25 @@ class Engine:
         ms, by = ctypes.c_float(), ctypes.c_double()
         _check(self._L.adc_profile_kernel(self._h, self.PROFILE_KERNELS[name], reps, ctypes.byref(ms), ctypes.byref(by)))
         return ms.value, by.value
+
+    # ---- output side of the reference's demo (main.cpp:147-230) -------------------------------
+    def render_disparity(self, disp: np.ndarray):
+        """(gray8 [H][W], jet_bgr [H][W][3], (min, max)): SaveDisparityMap's two images (main.cpp:180-207)."""
+        disp = np.ascontiguousarray(disp, np.float32).reshape(self.height, self.width)
+        gray = np.empty((self.height, self.width), np.uint8)
+        jet = np.empty((self.height, self.width, 3), np.uint8)
+        mm = np.empty(2, np.float32)
+        _check(self._L.adc_render_disparity(self._h, disp.ctypes.data, gray.ctypes.data, jet.ctypes.data, mm.ctypes.data))
+        return gray, jet, (float(mm[0]), float(mm[1]))
+
+    def disparity_cloud(self, left: np.ndarray, disp: np.ndarray) -> np.ndarray:
+        """[n][6] float32 records (x, y, |d|, r, g, b) of the valid pixels in raster order (main.cpp:209-230)."""
+        left = _img(left, (self.height, self.width, 3))
+        disp = np.ascontiguousarray(disp, np.float32).reshape(self.height, self.width)
+        cloud = np.empty((self.height * self.width, 6), np.float32)
+        n = ctypes.c_int32(0)
+        _check(self._L.adc_disparity_cloud(self._h, left.ctypes.data, disp.ctypes.data, cloud.ctypes.data, ctypes.byref(n)))
+        return cloud[:n.value].copy()
 
     # ---- debug taps -------------------------------------------------------------------------
     def debug_run(self, left, right, last_stage: str):

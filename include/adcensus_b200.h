@@ -122,6 +122,18 @@ int adc_get_config(const adc_engine* e, adc_config* out);
  * algorithmic_bytes (optional) receives the bytes one launch must move. */
 int adc_profile_kernel(adc_engine* e, int32_t kernel_id, int32_t reps, float* avg_ms, double* algorithmic_bytes);
 
+/* Output side of the reference's demo program (main.cpp, outside ADCensusStereo itself):
+ *   adc_render_disparity = ShowDisparityMap / SaveDisparityMap (main.cpp:147-207): the 8-bit image
+ *       uchar((|d| - min) / (max - min) * 255) with min / max over the valid pixels (0 where d is Invalid_Float),
+ *       and that image through cv::COLORMAP_JET as packed BGR.  gray8 [W*H], jet_bgr [W*H*3], min_max [2]; any
+ *       of the three may be NULL.  The file encoding (PNG) stays with the caller.
+ *   adc_disparity_cloud = SaveDisparityCloud (main.cpp:209-230): one record (x, y, |d|, r, g, b) as six floats per
+ *       valid pixel in raster order; `cloud` must hold W*H*6 floats, *n_points receives the record count.  The
+ *       text formatting ("%f %f %f %d %d %d") stays with the caller.
+ * Host pointers; the engine's lane 0 is used, so not concurrently with adc_match on the same engine. */
+int adc_render_disparity(adc_engine* e, const float* disp, uint8_t* gray8, uint8_t* jet_bgr, float* min_max);
+int adc_disparity_cloud(adc_engine* e, const uint8_t* img_left, const float* disp, float* cloud, int32_t* n_points);
+
 const char* adc_last_error(void);
 const char* adc_version(void);
 
