@@ -124,22 +124,20 @@ k_cost_volume(AdcDims dm, int ppc, const unsigned* __restrict__ bgrx,
         const unsigned cl = __ldg(left + row + x);
         const unsigned long long bl = __ldg(cen_l + row + x);
         float out[4];
+        const int i0 = (x - dm.dmin - 4 * q) - xr_base;   // staged index of xr = x - dmin - di for di = 4q; in [0, W+D-2] for real disparities
 #pragma unroll
         for (int j = 0; j < 4; j++) {
+            // branch-free: padding lanes (di >= D) and out-of-image matches compute on clamped operands and are
+            // overwritten by selects -- the per-disparity branches used to cost more than the arithmetic
             const int di = 4 * q + j;
-            float c = 1.0f;                         // out-of-image match: cost_computor.cpp:101-104
-            if (di >= dm.D) c = 0.0f;               // padding lane, never read as a cost
-            else {
-                const int i = (x - dm.dmin - di) - xr_base;   // staged index of xr = x - dmin - di, in [0, W+D-2]
-                const int si = (i & 3) * sq + (i >> 2);
-                const unsigned pix = s_bgr[si];
-                if (pix != 0xffffffffu) {
-                    const int sad = (int)__vsadu4(cl, pix);     // |dB| + |dG| + |dR| (4th byte is 0 in both)
-                    const int ham = __popcll(bl ^ s_cen[si]);
-                    c = __fsub_rn(s_ad[sad * CV_AD_REP + (lane & (CV_AD_REP - 1))], s_ce[ham * 32 + lane]);
-                }
-            }
-            out[j] = c;
+            const int i = max(i0 - j, 0);
+            const int si = (i & 3) * sq + (i >> 2);
+            const unsigned pix = s_bgr[si];
+            const int sad = min((int)__vsadu4(cl, pix), 765);           // |dB| + |dG| + |dR| (4th byte is 0 in both)
+            const int ham = __popcll(bl ^ s_cen[si]) & 63;
+            float c = __fsub_rn(s_ad[sad * CV_AD_REP + (lane & (CV_AD_REP - 1))], s_ce[ham * 32 + lane]);
+            c = pix == 0xffffffffu ? 1.0f : c;                          // out-of-image match: cost_computor.cpp:101-104
+            out[j] = di < dm.D ? c : 0.0f;                              // padding lane, never read as a cost
         }
         float4* dst = reinterpret_cast<float4*>(vol + (size_t)pair * dm.vol_stride + ((size_t)row + x) * dm.Dp) + q;
         *dst = make_float4(out[0], out[1], out[2], out[3]);

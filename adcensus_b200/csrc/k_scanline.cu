@@ -26,6 +26,7 @@
 // (bit d = d2(d) < tso); the bit string is a window of a per-row bit vector of the right image
 // stored mirrored, so that increasing d walks increasing bit positions.
 #include "adc_common.cuh"
+#include <stdlib.h>
 
 template <int K>
 struct Piece { static constexpr int G = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1); static constexpr int NP = K / G; };
@@ -124,9 +125,9 @@ k_so_records(AdcDims dm, int tso, const uint8_t* __restrict__ dmap,
     const unsigned* row = bitrows + (((size_t)pair * 4 + variant) * dm.H + y) * rw;
     const int j0 = W - 1 - x + dmin;           // bit position of d = 0  (xr = x - dmin)
     auto window = [&](int d0) -> unsigned {     // bits d0..d0+31 of the string, 0 where out of the row
-        const long long j = (long long)j0 + d0;
-        const long long wlo = j >> 5;            // floor division also for negative j
-        const int sh = (int)(j & 31);
+        const int j = j0 + d0;                   // |j| < W + D + 64: plain int
+        const int wlo = j >> 5;                  // arithmetic shift = floor division also for negative j
+        const int sh = j & 31;
         const unsigned a = (wlo >= 0 && wlo < rw) ? row[wlo] : 0u;
         const unsigned b = (wlo + 1 >= 0 && wlo + 1 < rw) ? row[wlo + 1] : 0u;
         return __funnelshift_r(a, b, sh);
@@ -327,6 +328,11 @@ int adc_launch_scanline(const AdcParams& P, const AdcWave& w, const float* src, 
     const int Dp = P.dm.Dp;
     int rc = 1;
 #define SO_GO(KK, LL) rc = launch_scanline_k<KK, LL>(P, w, src, dst, sx, sy, st)
+    static int lps = -1;       // ADC_SO_LPS=16: sixteen lanes per line also for Dp <= 64 (twice the warps, half the values per lane)
+    if (lps < 0) { const char* m = getenv("ADC_SO_LPS"); lps = m ? atoi(m) : 0; }
+    if (lps == 16 && Dp <= 64 && Dp > 32) {
+        switch ((Dp + 15) / 16) { case 3: SO_GO(3, 16); break; default: SO_GO(4, 16); }
+    } else
     if (Dp <= 64) {            // 8 lanes per line
         switch ((Dp + 7) / 8) { case 1: SO_GO(1, 8); break; case 2: SO_GO(2, 8); break; case 3: SO_GO(3, 8); break; case 4: SO_GO(4, 8); break;
                                 case 5: SO_GO(5, 8); break; case 6: SO_GO(6, 8); break; case 7: SO_GO(7, 8); break; default: SO_GO(8, 8); }

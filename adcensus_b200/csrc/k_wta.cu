@@ -297,13 +297,20 @@ k_wta_tile(AdcDims dm, int wpx, int3 pf, const float* __restrict__ vol, float* _
             for (int i = threadIdx.x; i < lines; i += blockDim.x) asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + (size_t)i * 32));
         }
     }
-    for (int i = threadIdx.x; i < ncols * Q; i += blockDim.x) {
-        const int c = i / Q, q = i - c * Q;
-        const int x = col_lo + c;
-        if (x >= 0 && x < dm.W) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(rowv + (size_t)x * dm.Dp) + q);
-            float* t = wt_tile + c * DS + 4 * q;
-            t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+    {   // one division per thread instead of one per element: a thread keeps its quad and strides over the columns
+        const bool even = (int)blockDim.x % Q == 0;
+        const int cstep = even ? (int)blockDim.x / Q : 1;
+        for (int i = threadIdx.x; i < ncols * Q; i += even ? cstep * Q : (int)blockDim.x) {
+            const int c = i / Q, q = i - c * Q;
+            for (int cc = c; cc < (even ? ncols : c + 1); cc += cstep) {
+                const int x = col_lo + cc;
+                if (x >= 0 && x < dm.W) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(rowv + (size_t)x * dm.Dp) + q);
+                    float* t = wt_tile + cc * DS + 4 * q;
+                    t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+                }
+            }
+            if (even) break;
         }
     }
     __syncthreads();
