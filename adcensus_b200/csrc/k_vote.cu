@@ -251,7 +251,8 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
     const long long room = (unsigned)__ldcg(cnt + 15);
     const bool use_fwd = !force_enum && (long long)ns * HW + room <= hist_stride;
     const int* fwd = reinterpret_cast<const int*>(hist + (size_t)ns * HW);
-    int* adj = reinterpret_cast<int*>(hist + (size_t)ns * HW) + (use_fwd ? room : 0);
+    // adjacency entry = (slot, pixel of that slot): a push needs both, and one 8-byte load is one L2 round trip less
+    int2* adj = reinterpret_cast<int2*>(reinterpret_cast<int*>(hist) + ((((long long)ns * HW + (use_fwd ? room : 0)) + 1) & ~1ll));   // 8-byte aligned
     unsigned long long t_start = 0;
     if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     if (use_fwd) {
@@ -295,15 +296,16 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
         __syncthreads();
     }
     const int n_adj = s_base;
-    const bool use_adj = use_fwd && s_fits && (long long)ns * HW + room + n_adj <= hist_stride;
+    const bool use_adj = use_fwd && s_fits && (long long)ns * HW + room + 1 + 2ll * n_adj <= hist_stride;
     // ---- fill (afterwards cur[t] = end of t's list = start of t + 1's)
     if (use_adj) {
         for (int s = wid; s < ns; s += VP_WARPS) {
             const int fb = fbase[s], fn = fcnt[s];
+            const int2 me = make_int2(s, pix(s));
             for (int k = lane; k < fn; k += 64) {
                 const int tA = __ldg(fwd + fb + k), tB = k + 32 < fn ? __ldg(fwd + fb + k + 32) : -1;
-                adj[atomicAdd(&cur[tA], 1)] = s;
-                if (tB >= 0) adj[atomicAdd(&cur[tB], 1)] = s;
+                adj[atomicAdd(&cur[tA], 1)] = me;
+                if (tB >= 0) adj[atomicAdd(&cur[tB], 1)] = me;
             }
         }
     }
@@ -334,12 +336,13 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
     auto push_adj = [&](int t, int q, int a, int b, int k, int phase) {
         // (global-memory cursors were advanced by L2 atomics: read them at L2)
         const int e0 = t > 0 ? (state_smem ? cur[t - 1] : __ldcg(cur + t - 1)) : 0, e1 = state_smem ? cur[t] : __ldcg(cur + t);
-        for (int e = e0 + lane; e < e1; e += 64) {
-            const int sA = adj[e];
-            const int sB = e + 32 < e1 ? adj[e + 32] : -1;
-            const int pA = pix(sA), pB = sB >= 0 ? pix(sB) : 0;
-            touch(sA, pA > q, a, b, k, phase);
-            if (sB >= 0) touch(sB, pB > q, a, b, k, phase);
+        for (int e = e0 + lane; e < e1; e += 128) {          // four entries per lane per trip, loads first
+            int2 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] = e + 32 * j < e1 ? adj[e + 32 * j] : make_int2(-1, 0);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (v[j].x >= 0) touch(v[j].x, v[j].y > q, a, b, k, phase);
         }
     };
     // Fallback: inverse region by enumeration.  p' = (px,py) has q = (qx,qy) in R(p') iff the horizontal arm of

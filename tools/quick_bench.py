@@ -50,5 +50,5 @@ eng = A.Engine(w, h, A.ADCensusOption())
 for _ in range(3):
     d = eng.match(left, right)
 c = eng.counters()
-print("voting counters [mism, occl, rounds, evals]:", c[:4], "warp0 us [work, barrier, commit, compact]:", c[12:16])
+print("voting counters [mism, occl, rounds, derives]:", c[:4], "list-build us:", c[4], "[changes, adjacency used, adjacency entries, forward-list room]:", c[12:16])
 print("single-pair stage ms (cost, aggr, so, wta, refine, out):", [round(x, 3) for x in eng.last_stage_ms()])
