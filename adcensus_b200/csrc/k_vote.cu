@@ -84,13 +84,15 @@ k_vote_slots(AdcDims dm, const int* __restrict__ vlist, int* __restrict__ counte
     }
 }
 
-// ---- region scan of one slot by one warp: eight rows per trip (two per half-warp pair x four), the first 32 columns of
-// each fetched before any is consumed (8 independent loads in flight per lane); the horizontal arms of all rows are
-// fetched up front (lane r holds rows r, r+32, r+64) and handed out by shuffle.  `visit` is called in warp-uniform
-// control flow (it may use warp collectives); -1 (an invalid pixel that is nobody's slot) stands in for "no pixel here".
-template <typename F>
+// ---- region scan of one slot by one warp.  A group of LPR lanes takes one region row, so a trip covers 4 x 32/LPR rows,
+// the first 2*LPR columns of each fetched before any is consumed (8 independent loads in flight per lane); the horizontal
+// arms of all rows are fetched up front (lane r holds rows r, r+32, r+64) and handed out by shuffle.  With LPR = 8 the
+// typical Cone region (a dozen rows of a dozen-odd pixels) is one trip.  `visit` is called in warp-uniform control flow
+// (it may use warp collectives); -1 (an invalid pixel that is nobody's slot) stands in for "no pixel here".
+template <int LPR, typename F>
 __device__ __forceinline__ void vote_scan_region(int p, int W, const uchar4* __restrict__ A, const uchar2* __restrict__ ALR,
                                                  const int* __restrict__ VS, int lane, F&& visit) {
+    constexpr int RPT = 32 / LPR;          // rows per step of a trip
     const int y = p / W, x = p - y * W;
     const uchar4 a = __ldg(A + p);
     const int top = a.z, rows = top + (int)a.w + 1;
@@ -103,12 +105,12 @@ __device__ __forceinline__ void vote_scan_region(int p, int W, const uchar4* __r
         if (ri < rows) v = __ldg(ALR + rbase + ri * W);
         ar[j] = (unsigned)v.x | ((unsigned)v.y << 8);
     }
-    const int half = lane >> 4, sub = lane & 15;
-    for (int r0 = 0; r0 < rows; r0 += 8) {
+    const int grp = lane / LPR, sub = lane % LPR;
+    for (int r0 = 0; r0 < rows; r0 += 4 * RPT) {
         int v0[4], v1[4], cl[4], ch[4], ro[4];
 #pragma unroll
         for (int t = 0; t < 4; t++) {
-            const int ri = r0 + 2 * t + half;
+            const int ri = r0 + RPT * t + grp;
             unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
             if (rows > 32) {
                 const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31), a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
@@ -118,21 +120,21 @@ __device__ __forceinline__ void vote_scan_region(int p, int W, const uchar4* __r
             cl[t] = -(int)(a2 & 255u) + sub;
             ch[t] = ri < rows ? (int)(a2 >> 8) : -0x10000;     // rows past the region: empty segment
             v0[t] = cl[t] <= ch[t] ? __ldg(VS + ro[t] + cl[t]) : -1;
-            v1[t] = cl[t] + 16 <= ch[t] ? __ldg(VS + ro[t] + cl[t] + 16) : -1;
+            v1[t] = cl[t] + LPR <= ch[t] ? __ldg(VS + ro[t] + cl[t] + LPR) : -1;
         }
         int more = 0;
 #pragma unroll
-        for (int t = 0; t < 4; t++) more = max(more, (ch[t] - cl[t]) / 16);
-        more = __reduce_max_sync(0xffffffffu, more);          // 16-column chunks the widest row of the trip needs, minus one
+        for (int t = 0; t < 4; t++) more = max(more, (ch[t] - cl[t]) / LPR);
+        more = __reduce_max_sync(0xffffffffu, more);          // LPR-column chunks the widest row of the trip needs, minus one
 #pragma unroll
         for (int t = 0; t < 4; t++) visit(v0[t]);
         if (more >= 1) {
 #pragma unroll
             for (int t = 0; t < 4; t++) visit(v1[t]);
         }
-        for (int k = 2; k <= more; k++) {                     // rows wider than 32 pixels (rare)
+        for (int k = 2; k <= more; k++) {                     // wider rows
 #pragma unroll
-            for (int t = 0; t < 4; t++) visit(cl[t] + 16 * k <= ch[t] ? __ldg(VS + ro[t] + cl[t] + 16 * k) : -1);
+            for (int t = 0; t < 4; t++) visit(cl[t] + LPR * k <= ch[t] ? __ldg(VS + ro[t] + cl[t] + LPR * k) : -1);
         }
     }
 }
@@ -171,7 +173,7 @@ k_vote_scan(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restri
             fb = __shfl_sync(0xffffffffu, fb, 0);
         }
         __syncwarp();
-        vote_scan_region(p, W, A, ALR, VS, lane, [&](int v) {
+        vote_scan_region<8>(p, W, A, ALR, VS, lane, [&](int v) {
             if (v >= 0 && v < D) atomicAdd(&hs[v], 1);
             if (use_fwd) {
                 const bool edge = v < -1 && -v - 2 != s;
@@ -255,16 +257,29 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
     int2* adj = reinterpret_cast<int2*>(reinterpret_cast<int*>(hist) + ((((long long)ns * HW + (use_fwd ? room : 0)) + 1) & ~1ll));   // 8-byte aligned
     unsigned long long t_start = 0;
     if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
-    if (use_fwd) {
-        for (int s = wid; s < ns; s += VP_WARPS) {
-            const int fb = fbase[s], fn = fcnt[s];
-            for (int k = lane; k < fn; k += 64) {
-                const int tA = __ldg(fwd + fb + k), tB = k + 32 < fn ? __ldg(fwd + fb + k + 32) : -1;
-                atomicAdd(&cur[tA + 1], 1);                          // length of t's list, kept at index t + 1
-                if (tB >= 0) atomicAdd(&cur[tB + 1], 1);
+    // Both passes over the forward lists: a warp takes 32 consecutive slots at a time (their list descriptors in one
+    // coalesced load, handed out by shuffle), two lists per trip, two entries per list and lane in flight.
+    auto for_each_edge = [&](auto&& f) {
+        for (int base = wid * 32; base < ns; base += VP_WARPS * 32) {
+            const int sl = base + lane;
+            const int my_fb = sl < ns ? fbase[sl] : 0, my_fn = sl < ns ? fcnt[sl] : 0, my_p = sl < ns ? pix(sl) : 0;
+            for (int j = 0; j < 32; j += 2) {
+                const int fbA = __shfl_sync(0xffffffffu, my_fb, j), fnA = __shfl_sync(0xffffffffu, my_fn, j);
+                const int fbB = __shfl_sync(0xffffffffu, my_fb, j + 1), fnB = __shfl_sync(0xffffffffu, my_fn, j + 1);
+                const int pA = __shfl_sync(0xffffffffu, my_p, j), pB = __shfl_sync(0xffffffffu, my_p, j + 1);
+                const int nmax = max(fnA, fnB);
+                for (int k = lane; k < nmax; k += 64) {
+                    const int a0 = k < fnA ? __ldg(fwd + fbA + k) : -1, a1 = k + 32 < fnA ? __ldg(fwd + fbA + k + 32) : -1;
+                    const int b0 = k < fnB ? __ldg(fwd + fbB + k) : -1, b1 = k + 32 < fnB ? __ldg(fwd + fbB + k + 32) : -1;
+                    if (a0 >= 0) f(a0, base + j, pA);
+                    if (a1 >= 0) f(a1, base + j, pA);
+                    if (b0 >= 0) f(b0, base + j + 1, pB);
+                    if (b1 >= 0) f(b1, base + j + 1, pB);
+                }
             }
         }
-    }
+    };
+    if (use_fwd) for_each_edge([&](int t, int, int) { atomicAdd(&cur[t + 1], 1); });   // length of t's list, kept at index t + 1
     __syncthreads();
     // ---- inclusive prefix sum over cur[0..ns]: cur[t] = start of t's list, cur[ns] = number of entries
     if (tid == 0) { s_base = 0; s_fits = 1; }
@@ -298,17 +313,7 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
     const int n_adj = s_base;
     const bool use_adj = use_fwd && s_fits && (long long)ns * HW + room + 1 + 2ll * n_adj <= hist_stride;
     // ---- fill (afterwards cur[t] = end of t's list = start of t + 1's)
-    if (use_adj) {
-        for (int s = wid; s < ns; s += VP_WARPS) {
-            const int fb = fbase[s], fn = fcnt[s];
-            const int2 me = make_int2(s, pix(s));
-            for (int k = lane; k < fn; k += 64) {
-                const int tA = __ldg(fwd + fb + k), tB = k + 32 < fn ? __ldg(fwd + fb + k + 32) : -1;
-                adj[atomicAdd(&cur[tA], 1)] = me;
-                if (tB >= 0) adj[atomicAdd(&cur[tB], 1)] = me;
-            }
-        }
-    }
+    if (use_adj) for_each_edge([&](int t, int s, int p) { adj[atomicAdd(&cur[t], 1)] = make_int2(s, p); });
     __syncthreads();
     if (tid == 0) {
         unsigned long long t1;
