@@ -56,6 +56,16 @@ __device__ __forceinline__ float adc_key2f(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// Function attributes and __device__ / __constant__ symbols exist once per device: one-time set-up is keyed by the
+// current device (one process may own engines on several GPUs).  Racing threads at worst repeat the same set-up.
+inline bool adc_first_time_on_device(bool (&done)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (done[dev & 63]) return false;
+    done[dev & 63] = true;
+    return true;
+}
+
 // ---- launchers (defined in the k_*.cu files; all asynchronous on `st`) -------------------------
 struct AdcWave {            // device pointers of one wave (S pairs)
     int S;                  // active pairs in this launch

@@ -1037,11 +1037,10 @@ int adc_launch_median(const AdcParams& P, const AdcWave& w, const float* in, flo
     const int rows = P.dm.H <= MED_THREADS ? 1 : 2;
     const int threads = std::min(MED_THREADS, ((P.dm.H + rows - 1) / rows + 31) / 32 * 32);
     const size_t smem = ((size_t)P.dm.H * 4 + (size_t)threads * rows * MED_PF * 2) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};
+    if (adc_first_time_on_device(attr_done)) {
         cudaFuncSetAttribute(k_median_wavefront<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_median_wavefront<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
     }
     if (rows == 1) k_median_wavefront<1><<<w.S, threads, smem, st>>>(P.dm, in, out);
     else           k_median_wavefront<2><<<w.S, threads, smem, st>>>(P.dm, in, out);

@@ -560,10 +560,9 @@ bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st,
     if (cap_override < 0) { const char* m = getenv("ADC_VOTE_SLOTCAP"); cap_override = m ? atoi(m) : 0; }
     if (cap_override > 0 && cap_override < slot_cap) slot_cap = cap_override & ~15;
     const size_t smem = fixed + 2 * (size_t)slot_cap + ((size_t)slot_cap + 1) * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};
+    if (adc_first_time_on_device(attr_done)) {
         cudaFuncSetAttribute(k_vote_push, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);   // (+ static < 227 KB)
-        attr_done = true;
     }
     k_vote_push<<<w.S, VP_THREADS, smem, st>>>(P, w.vote_alr, w.vote_atbT, w.vote_pslotT, w.pend, hist, dm.vol_stride,
                                               w.vote_off, w.vote_val, w.vote_dirtyb, w.vlist, w.counters, w.last_eval,

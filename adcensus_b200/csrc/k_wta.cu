@@ -380,10 +380,9 @@ int adc_launch_wta(const AdcParams& P, const AdcWave& w, const float* vol, cudaS
     while (wpx > 32 && (size_t)(wpx + extra) * (P.dm.Dp + 1) * sizeof(float) > 64 * 1024) wpx >>= 1;
     const size_t tile_bytes = (size_t)(wpx + extra) * (P.dm.Dp + 1) * sizeof(float);
     if (tile_bytes <= 200 * 1024) {
-        static bool attr_done = false;
-        if (!attr_done) {
+        static bool attr_done[64] = {};
+        if (adc_first_time_on_device(attr_done)) {
             cudaFuncSetAttribute(k_wta_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_done = true;
         }
         dim3 grid((P.dm.W + wpx - 1) / wpx, P.dm.H, w.S);
         const long long pfd = 148 * 4;
