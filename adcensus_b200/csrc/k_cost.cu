@@ -14,15 +14,11 @@
 #define CT_HX 3
 #define CT_HY 4
 
-// The three products have 256 possible values each: they come from tables (the same IEEE double products, computed once on
-// the host), which leaves two double adds per pixel on the FP64 pipe instead of three conversions, three multiplies and two
-// adds -- the kernel was bound by exactly that pipe.
-__device__ double g_gray_lut[3 * 256];   // [0..255] r*0.299, [256..511] g*0.587, [512..767] b*0.114
-static bool g_gray_lut_ready[64] = {};   // per device (a __device__ symbol has one instance per device)
-
-__device__ __forceinline__ uint8_t gray_of(const uint8_t* __restrict__ px, const double* __restrict__ lut) {
-    const int b = __ldg(px), g = __ldg(px + 1), r = __ldg(px + 2);
-    const double v = __dadd_rn(__dadd_rn(lut[r], lut[256 + g]), lut[512 + b]);
+// (A table of the 3 x 256 possible products, which leaves two double adds per pixel, was measured: the per-CTA copy of the
+//  table into shared memory costs more than the three multiplies it saves -- 220 us against 201 us per wave of 32 pairs.)
+__device__ __forceinline__ uint8_t gray_of(const uint8_t* __restrict__ px) {
+    const double b = (double)__ldg(px), g = (double)__ldg(px + 1), r = (double)__ldg(px + 2);
+    const double v = __dadd_rn(__dadd_rn(__dmul_rn(r, 0.299), __dmul_rn(g, 0.587)), __dmul_rn(b, 0.114));
     return (uint8_t)__double2int_rz(v);
 }
 
@@ -30,9 +26,6 @@ __global__ void __launch_bounds__(CT_W* CT_H)
 k_gray_census(AdcDims dm, const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray,
               unsigned long long* __restrict__ census, unsigned* __restrict__ bgrx) {
     __shared__ uint8_t tile[CT_H + 2 * CT_HY][CT_W + 2 * CT_HX + 2];
-    __shared__ double s_lut[3 * 256];
-    for (int i = threadIdx.y * CT_W + threadIdx.x; i < 3 * 256; i += CT_W * CT_H) s_lut[i] = g_gray_lut[i];
-    __syncthreads();
     const int img = blockIdx.z;  // pair*2 + view
     const uint8_t* src = bgr + (size_t)img * dm.N * 3;
     uint8_t* g_out = gray + (size_t)img * dm.N;
@@ -44,7 +37,7 @@ k_gray_census(AdcDims dm, const uint8_t* __restrict__ bgr, uint8_t* __restrict__
         const int ty = i / TW, tx = i - ty * TW;
         const int gx = x0 + tx - CT_HX, gy = y0 + ty - CT_HY;
         uint8_t v = 0;
-        if (gx >= 0 && gx < dm.W && gy >= 0 && gy < dm.H) v = gray_of(src + ((size_t)gy * dm.W + gx) * 3, s_lut);
+        if (gx >= 0 && gx < dm.W && gy >= 0 && gy < dm.H) v = gray_of(src + ((size_t)gy * dm.W + gx) * 3);
         tile[ty][tx] = v;
     }
     __syncthreads();
@@ -70,11 +63,6 @@ k_gray_census(AdcDims dm, const uint8_t* __restrict__ bgr, uint8_t* __restrict__
 }
 
 void adc_launch_gray_census(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
-    if (adc_first_time_on_device(g_gray_lut_ready)) {   // (r*0.299 etc. exactly as cost_computor.cpp:69 multiplies them, in double)
-        double lut[3 * 256];
-        for (int v = 0; v < 256; v++) { lut[v] = (double)v * 0.299; lut[256 + v] = (double)v * 0.587; lut[512 + v] = (double)v * 0.114; }
-        cudaMemcpyToSymbol(g_gray_lut, lut, sizeof(lut));
-    }
     dim3 grid((P.dm.W + CT_W - 1) / CT_W, (P.dm.H + CT_H - 1) / CT_H, w.S * 2), block(CT_W, CT_H);
     k_gray_census<<<grid, block, 0, st>>>(P.dm, w.bgr, w.gray, w.census, w.bgrx);
     ++*launches;

@@ -284,7 +284,7 @@ def run_gpu_arm(args):
                 "frac": kern[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "note": "algorithmic bytes per launch = (2V + 6N) per pair x pairs per launch, V = 4*H*W*D (SURVEY 8d); "
                         "traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture "
-                        "(profiles/r1_ncu_full_v26_summary.csv); kernel timed alone with CUDA events on the engine's stream"}
+                        "(profiles/r1_ncu_full_v32_summary.csv); kernel timed alone with CUDA events on the engine's stream"}
         total_maps = world * n * args.steps
         value = total_maps / (ms_dev * 1e-3)
         e2e_v = total_maps / (ms_e2e * 1e-3)
