@@ -79,6 +79,7 @@ struct adc_engine {
     float* d_lut_cen = nullptr;
     double* d_rays = nullptr;  // [32]: sin[16], cos[16]
     short2* d_ray_off = nullptr;  // [16][max_search] integer ray offsets, when verified exact for this image size
+    bool pipelined = false;            // adc_set_pipelined: batch calls do not join the caller's stream themselves
     unsigned long long launches = 0;
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t ev_stage[8] = {};
@@ -394,7 +395,11 @@ int run_batch(adc_engine* e, int n, SrcKind kind, const uint8_t* const* lp, cons
         }
         CK(cudaEventRecord(ln.ev_done, ln.st));
     }
-    for (int li = 0; li < std::min(nl, n_waves); li++) CK(cudaStreamWaitEvent(user, e->lanes[li].ev_done, 0));
+    // join: the caller's stream waits for every lane -- unless the engine is in pipelined mode, where consecutive
+    // batch calls flow into each other (a lane starts the next call's wave while other lanes still finish the
+    // previous call's) and the caller joins once with adc_join
+    if (!e->pipelined || (!pinned && kind != SRC_DEVICE_STRIDED))
+        for (int li = 0; li < std::min(nl, n_waves); li++) CK(cudaStreamWaitEvent(user, e->lanes[li].ev_done, 0));
     if (!pinned && kind != SRC_DEVICE_STRIDED)
         for (auto& ln : e->lanes) { int rc = drain_lane(e, ln); if (rc) return rc; }
     return ADC_OK;
@@ -591,6 +596,19 @@ int adc_synchronize(adc_engine* e) {
     CK(cudaSetDevice(e->cfg.device));
     for (auto& ln : e->lanes) CK(cudaStreamSynchronize(ln.st));
     CK(cudaStreamSynchronize(e->main_st));
+    return ADC_OK;
+}
+
+int adc_set_pipelined(adc_engine* e, int32_t on) {
+    if (!e) return fail(ADC_ERR_ARG, "adc_set_pipelined: engine is NULL");
+    e->pipelined = on != 0;
+    return ADC_OK;
+}
+
+int adc_join(adc_engine* e, void* stream) {
+    if (!e) return fail(ADC_ERR_ARG, "adc_join: engine is NULL");
+    CK(cudaSetDevice(e->cfg.device));
+    for (auto& ln : e->lanes) CK(cudaStreamWaitEvent((cudaStream_t)stream, ln.ev_done, 0));
     return ADC_OK;
 }
 

@@ -93,6 +93,8 @@ def load_library() -> ctypes.CDLL:
     L.adc_last_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 6)]
     L.adc_get_config.argtypes = [vp, ctypes.POINTER(_Config)]
     L.adc_profile_kernel.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]
+    L.adc_set_pipelined.argtypes = [vp, i32]
+    L.adc_join.argtypes = [vp, vp]
     L.adc_render_disparity.argtypes = [vp, f32p, u8p, u8p, f32p]
     L.adc_disparity_cloud.argtypes = [vp, u8p, f32p, f32p, ctypes.POINTER(ctypes.c_int32)]
     L.adc_last_error.restype = ctypes.c_char_p
@@ -201,6 +203,14 @@ class Engine:
         ms, by = ctypes.c_float(), ctypes.c_double()
         _check(self._L.adc_profile_kernel(self._h, self.PROFILE_KERNELS[name], reps, ctypes.byref(ms), ctypes.byref(by)))
         return ms.value, by.value
+
+    # ---- streaming: consecutive async batch calls without a drain in between -------------------
+    def set_pipelined(self, on: bool = True):
+        _check(self._L.adc_set_pipelined(self._h, 1 if on else 0))
+
+    def join(self, stream: int = 0):
+        """Makes `stream` wait for everything submitted so far (required before results are read in pipelined mode)."""
+        _check(self._L.adc_join(self._h, stream))
 
     # ---- output side of the reference's demo (main.cpp:147-230) -------------------------------
     def render_disparity(self, disp: np.ndarray):

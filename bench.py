@@ -195,6 +195,7 @@ def run_gpu_arm(args):
 
     opt = A.ADCensusOption(min_disparity=dmin, max_disparity=dmax)
     eng = A.Engine(w, h, opt, device=local, wave_pairs=args.wave_pairs, lanes=args.lanes)
+    eng.set_pipelined(not args.no_pipeline)
     N = w * h
     h_left = torch.from_numpy(np.repeat(left[None], n, 0) if lefts is None else lefts).pin_memory()
     h_right = torch.from_numpy(np.repeat(right[None], n, 0) if rights is None else rights).pin_memory()
@@ -216,6 +217,7 @@ def run_gpu_arm(args):
         e0.record(st)
         for _ in range(steps):
             fn()
+        eng.join(st.cuda_stream)        # pipelined engine: the K steps flow into each other, the join is inside the timed region
         e1.record(st)
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -231,6 +233,7 @@ def run_gpu_arm(args):
 
     for _ in range(max(3, args.warmup)):
         dev_step()
+    eng.join(st.cuda_stream)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -238,6 +241,7 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if sampler else None
     for _ in range(2):
         e2e_step()
+    eng.join(st.cuda_stream)
     ms_e2e, _ = timed(e2e_step, args.steps)
 
     # correctness guard inside the bench: every map of the batch must equal the single-pair result
@@ -296,6 +300,7 @@ def run_gpu_arm(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl_name, "pairs_per_step_per_gpu": n, "width": w, "height": h, "disparities": dmax - dmin,
                            "wave_pairs": eng.wave_pairs, "lanes": eng.lanes,
+                           "steps_pipelined": not args.no_pipeline,
                            "l2_policy": "no flush needed: each step streams the whole batch of images and several GB of cost volumes per wave, far beyond the 126 MB L2",
                            "parallelism": f"dp{world} (independent pairs, no data-path collective)"},
                 "e2e": {"value": round(e2e_v, 2), "unit": "maps/s", "h2d_bytes_per_step": n * 2 * N * 3,
@@ -322,6 +327,8 @@ def main():
     ap.add_argument("--wave-pairs", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="join the stream after every step (adc_set_pipelined off): each step then drains the engine")
     ap.add_argument("--workload", default="cone", choices=["cone", "kitti", "1080p"],
                     help="cone = BASELINE configs[1] (the contract metric); kitti / 1080p = configs[2] / configs[3] (extra lines)")
     args = ap.parse_args()

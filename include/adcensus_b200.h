@@ -103,6 +103,15 @@ int adc_match_batch_device(adc_engine* e, int32_t n, const uint8_t* d_left, cons
 int adc_match_batch_pinned_async(adc_engine* e, int32_t n, const uint8_t* left, const uint8_t* right,
                                  float* disp, void* stream);
 
+/* Streaming use: by default every async batch call makes `stream` wait for all of its work, so
+ * two calls in a row drain the engine in between (the last waves of a call end in latency-bound refinement kernels with
+ * nothing left to overlap them with).  In pipelined mode a batch call returns without that join: the next call's first
+ * waves start on the lanes that are already free, and the caller makes its stream wait once, with adc_join, before it
+ * touches any result.  Inputs are still consumed in stream order of the call; outputs of a call are complete only
+ * after adc_join (or adc_synchronize).  Has no effect on the synchronous entry points. */
+int adc_set_pipelined(adc_engine* e, int32_t on);
+int adc_join(adc_engine* e, void* stream);
+
 void* adc_host_alloc(size_t bytes);  /* pinned host memory (cudaHostAlloc) */
 void  adc_host_free(void* p);
 int   adc_synchronize(adc_engine* e);

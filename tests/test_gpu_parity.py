@@ -265,3 +265,31 @@ def test_voting_fallback_paths(tmp_path, env):
     env = dict(os.environ, **env)
     r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_pipelined_batches(cone):
+    """adc_set_pipelined: three async batch calls in a row without a join in between (different inputs, different output
+    buffers, more pairs than one wave), one adc_join at the end; every map must equal the single-pair result."""
+    import torch
+    left, right = cone
+    h, w, _ = left.shape
+    eng = _engine(w, h, T.default_option(), wave_pairs=4, lanes=3)
+    single = [eng.match(left, right), eng.match(right, left), eng.match(left[:, ::-1].copy(), right[:, ::-1].copy())]
+    ins = [(left, right), (right, left), (left[:, ::-1].copy(), right[:, ::-1].copy())]
+    n = 10
+    st = torch.cuda.current_stream()
+    eng.set_pipelined(True)
+    outs, keep = [], []
+    for l, r in ins:
+        dl = torch.from_numpy(np.repeat(l[None], n, 0)).cuda()
+        dr = torch.from_numpy(np.repeat(r[None], n, 0)).cuda()
+        dd = torch.zeros((n, h, w), dtype=torch.float32, device="cuda")
+        keep.append((dl, dr))
+        eng.match_batch_device(n, dl.data_ptr(), dr.data_ptr(), dd.data_ptr(), st.cuda_stream)
+        outs.append(dd)
+    eng.join(st.cuda_stream)
+    torch.cuda.synchronize()
+    for want, got in zip(single, outs):
+        assert (got.cpu().numpy().view(np.uint32) == want.view(np.uint32)[None]).all()
+    eng.set_pipelined(False)
+    eng.close()
