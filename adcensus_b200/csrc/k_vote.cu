@@ -336,7 +336,9 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
         unsigned* h = hist + (size_t)s * HW;
         if (a < D) atomicSub(h + (a >> 1), 1u << ((a & 1) * 16));
         if (b < D) atomicAdd(h + (b >> 1), 1u << ((b & 1) * 16));
-        if (!(f & VP_FLAG_DIRTY)) flg[s] = (uint8_t)VP_FLAG_DIRTY;   // (all writers write the same value)
+        // (racecheck flags this byte: concurrent pushes may read and set the same slot's flag -- every writer stores the same
+        //  value into its own byte and a reader that still sees 0 merely stores it again; the flags are consumed after a barrier)
+        if (!(f & VP_FLAG_DIRTY)) flg[s] = (uint8_t)VP_FLAG_DIRTY;
     };
     auto push_adj = [&](int t, int q, int a, int b, int k, int phase) {
         // (global-memory cursors were advanced by L2 atomics: read them at L2)
@@ -430,6 +432,7 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
             if (n == 0) continue;
             bool any_change = false;
             while (true) {
+                __syncthreads();   // (everybody has read the previous round's counters)
                 if (tid == 0) { s_nwork = 0; s_nchg = 0; }
                 __syncthreads();
                 // ---- collect the pixels of this list whose histogram changed since their last derive
