@@ -144,3 +144,15 @@ def test_two_rank_scatter_gather_gloo(tmp_path):
     for p, (so, se) in zip(procs, outs):
         assert p.returncode == 0, se[-2000:]
     assert "SHARD_OK" in outs[0][0]
+
+
+def test_division_sequence_is_exact(tmp_path):
+    """The aggregation's x / n (cross_aggregator.cpp:389) runs on the device as the compiler's IEEE fast-path sequence with the
+    reciprocal hoisted (adc_div4, k_aggregate.cu).  tests/c/div_sequence.c replays that sequence on the CPU for every divisor
+    1..65535, a dense sample of numerators and every approximate reciprocal within 3 ulp of 1/n: all quotients must be the
+    IEEE ones."""
+    import subprocess
+    exe = tmp_path / "div_sequence"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), str(T.REPO / "tests" / "c" / "div_sequence.c"), "-lm"], check=True)
+    r = subprocess.run([str(exe), "300", "3"], capture_output=True, text=True)
+    assert r.returncode == 0 and "total 0" in r.stdout, r.stdout

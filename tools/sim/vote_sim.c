@@ -4,6 +4,7 @@
 #include <string.h>
 #include <math.h>
 #include <stdint.h>
+static const char *sim_path(const char *name) { static char buf[4][512]; static int k; const char *d = getenv("ADC_SIM_DIR"); char *b = buf[k++ & 3]; snprintf(b, 512, "%s/%s", d ? d : "/tmp/sim", name); return b; }
 #define W 450
 #define H 375
 #define N (W*H)
@@ -42,11 +43,11 @@ static int eval(int p, const uint8_t *o, const uint8_t *nw) {
 int main(int argc, char **argv) {
     int mode = argc > 1 ? atoi(argv[1]) : 0;
     int TILE = argc > 2 ? atoi(argv[2]) : 16; int BAND = argc > 3 ? atoi(argv[3]) : 100000; int fmode = argc > 4 ? atoi(argv[4]) : 0;
-    rd("/tmp/sim/disp.bin", disp0, sizeof disp0); rd("/tmp/sim/disp_vote.bin", dref, sizeof dref);
-    rd("/tmp/sim/arms.bin", arms, sizeof arms); rd("/tmp/sim/suph.bin", suph, sizeof suph);
+    rd(sim_path("disp.bin"), disp0, sizeof disp0); rd(sim_path("disp_vote.bin"), dref, sizeof dref);
+    rd(sim_path("arms.bin"), arms, sizeof arms); rd(sim_path("suph.bin"), suph, sizeof suph);
     static int tmp[N];
     for (int k = 0; k < 2; k++) {
-        int n = rdlist(k ? "/tmp/sim/oc.bin" : "/tmp/sim/mm.bin", tmp);
+        int n = rdlist(k ? sim_path("oc.bin") : sim_path("mm.bin"), tmp);
         nlist[k] = 0;
         for (int i = 0; i < n; i++) if (suph[tmp[i]] > irv_ts) listv[k][nlist[k]++] = tmp[i];
     }
