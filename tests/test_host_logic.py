@@ -153,6 +153,6 @@ def test_division_sequence_is_exact(tmp_path):
     IEEE ones."""
     import subprocess
     exe = tmp_path / "div_sequence"
-    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), str(T.REPO / "tests" / "c" / "div_sequence.c"), "-lm"], check=True)
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), str(ROOT / "tests" / "c" / "div_sequence.c"), "-lm"], check=True)
     r = subprocess.run([str(exe), "300", "3"], capture_output=True, text=True)
     assert r.returncode == 0 and "total 0" in r.stdout, r.stdout
