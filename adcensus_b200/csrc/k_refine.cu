@@ -80,7 +80,10 @@ void adc_launch_outlier(const AdcParams& P, const AdcWave& w, cudaStream_t st, u
 }
 
 // =============================================================================================
-// 2. Iterative region voting.  Reference: 5 iterations x {mismatch list, occlusion list}; within a
+// 2. Iterative region voting -- the PULL form.  The default path is the incremental-histogram (push) form in
+//    k_vote.cu; the kernels below remain as the fallback for configurations that path does not take (more than
+//    254 disparities, arms longer than 127) and as the A/B reference (ADC_VOTE_MODE=1 / 2 / 3).
+//    Reference: 5 iterations x {mismatch list, occlusion list}; within a
 //    sweep pixels are visited in list (= raster) order and a filled pixel is immediately visible to
 //    later ones (Gauss-Seidel).  Exact parallel form ("raster-aware fixed point"): keep OLD (state at
 //    sweep start) and NEW.  Repeatedly recompute pending pixels p of the list in parallel, reading
