@@ -99,6 +99,7 @@ struct AdcWave {            // device pointers of one wave (S pairs)
     int* vote_state;        // [S][N]     region voting: disparity index of a valid pixel, -1 invalid, -(slot+2) pending
     int* vote_deg;          // [S][N]     region voting: adjacency list lengths / fill cursors per slot
     int* vote_off;          // [S][N+1]   region voting: adjacency list offsets (CSR by target slot)
+    unsigned* vote_hist;    // [S][vol_stride] region voting: histograms + forward lists + adjacency (= volB unless the lane refines asynchronously)
     const float* lut_ad;    // [766]  (1 - exp(-(s/3)/lambda_ad)) + 1, host libm expf
     const float* lut_cen;   // [64]   exp(-h/lambda_census)
     const double* ray_sin; const double* ray_cos; // [16] host libm sin/cos of the accumulated angles

@@ -57,6 +57,13 @@ struct Lane {
     AdcWave w{};                       // device pointers, capacity S pairs
     uint8_t* pin_in = nullptr;         // [S][2][N*3] pinned staging (pageable callers only)
     float* pin_out = nullptr;          // [S][N]
+    // async_refine (experimental): the refinement stage of a wave runs on st_ref on one of two buffer sets while st already
+    // streams the volumes of the lane's next wave.  ev_vol: the wave's volume stage (up to WTA) is done; ev_free: the wave has
+    // left the set (its result copy-out included).
+    cudaStream_t st_ref = nullptr;
+    struct RefSet { void* arena = nullptr; AdcWave w{}; cudaEvent_t ev_vol = nullptr, ev_free = nullptr; } rs[2];
+    unsigned long long wave_no = 0;
+    int last_set = -1;
     // pending copy-out of a staged wave (pageable callers)
     int drain_n = 0;
     float* const* drain_ptrs = nullptr;
@@ -144,6 +151,45 @@ size_t carve_lane(void* base, const AdcDims& dm, int S, AdcWave* w) {
     t.so_rec = c.take<unsigned>((size_t)S * adc_so_rec_bytes(dm) / 4);
     t.tile_stamp = c.take<int>((size_t)S * ((dm.W + 15) / 16) * ((dm.H + 15) / 16));
     t.last_eval = c.take<int>((size_t)S * N);
+    t.vote_hist = reinterpret_cast<unsigned*>(t.volB);   // idle after the last scanline pass
+    if (w) *w = t;
+    return c.off;
+}
+
+// Carves (or sizes) one refinement buffer set of an async_refine lane: everything the kernels after WTA read or write,
+// plus what the volume stage produces for them (packed images, arms, support counts, the two disparity maps).
+size_t carve_refset(void* base, const AdcDims& dm, int S, AdcWave* w) {
+    Carver c(base);
+    const size_t N = (size_t)dm.N;
+    AdcWave t{};
+    t.bgr = c.take<uint8_t>((size_t)S * 2 * N * 3);
+    t.bgrx = c.take<unsigned>((size_t)S * 2 * N);
+    t.arms = c.take<uchar4>((size_t)S * N);
+    t.sup_h = c.take<uint16_t>((size_t)S * N);
+    t.sup_v = c.take<uint16_t>((size_t)S * N);
+    t.disp_l = c.take<float>((size_t)S * N);
+    t.disp_r = c.take<float>((size_t)S * N);
+    t.disp_t = c.take<float>((size_t)S * N);
+    t.label = c.take<uint8_t>((size_t)S * N);
+    t.flag = c.take<uint8_t>((size_t)S * N);
+    t.pend = c.take<int>((size_t)S * 2 * N);
+    t.vlist = c.take<int>((size_t)S * 2 * N);
+    t.counters = c.take<int>((size_t)S * ADC_CNT);
+    t.vote_dq = c.take<uint8_t>((size_t)S * 2 * N);
+    t.vote_alr = c.take<uchar2>((size_t)S * N);
+    t.vote_dirty = c.take<int2>((size_t)S * N);
+    t.vote_atbT = c.take<uchar2>((size_t)S * N);
+    t.vote_pslotT = c.take<int>((size_t)S * N);
+    t.vote_val = c.take<uint8_t>((size_t)S * N);
+    t.vote_dirtyb = c.take<uint8_t>((size_t)S * N);
+    t.vote_dead = c.take<uint8_t>((size_t)S * N);
+    t.vote_state = c.take<int>((size_t)S * N);
+    t.vote_deg = c.take<int>((size_t)S * N);
+    t.vote_off = c.take<int>((size_t)S * (N + 1));
+    t.rowcnt = c.take<int>((size_t)S * 2 * dm.H);
+    t.tile_stamp = c.take<int>((size_t)S * ((dm.W + 15) / 16) * ((dm.H + 15) / 16));
+    t.last_eval = c.take<int>((size_t)S * N);
+    t.vote_hist = c.take<unsigned>((size_t)S * dm.vol_stride);
     if (w) *w = t;
     return c.off;
 }
@@ -218,8 +264,18 @@ int upload_tables(adc_engine* e) {
     return ADC_OK;
 }
 
-AdcWave wave_view(const adc_engine* e, const Lane& ln, int nS) {
+AdcWave wave_view(const adc_engine* e, const Lane& ln, int nS, int set = -1) {
     AdcWave w = ln.w;
+    if (set >= 0) {   // async_refine: the wave's refinement buffers come from the set, the volume-stage buffers from the lane
+        const AdcWave& r = ln.rs[set].w;
+        w.bgr = r.bgr; w.bgrx = r.bgrx; w.arms = r.arms; w.sup_h = r.sup_h; w.sup_v = r.sup_v;
+        w.disp_l = r.disp_l; w.disp_r = r.disp_r; w.disp_t = r.disp_t; w.label = r.label; w.flag = r.flag;
+        w.pend = r.pend; w.vlist = r.vlist; w.counters = r.counters; w.vote_dq = r.vote_dq; w.vote_alr = r.vote_alr;
+        w.vote_dirty = r.vote_dirty; w.vote_atbT = r.vote_atbT; w.vote_pslotT = r.vote_pslotT; w.vote_val = r.vote_val;
+        w.vote_dirtyb = r.vote_dirtyb; w.vote_dead = r.vote_dead; w.vote_state = r.vote_state; w.vote_deg = r.vote_deg;
+        w.vote_off = r.vote_off; w.rowcnt = r.rowcnt; w.tile_stamp = r.tile_stamp; w.last_eval = r.last_eval;
+        w.vote_hist = r.vote_hist;
+    }
     w.S = nS;
     w.lut_ad = e->d_lut_ad;
     w.lut_cen = e->d_lut_cen;
@@ -232,10 +288,14 @@ AdcWave wave_view(const adc_engine* e, const Lane& ln, int nS) {
 // Enqueues the whole pipeline for the nS pairs whose images already sit in ln.w.bgr.  Stops after
 // `last_stage` (ADC_STAGE_MEDIAN = everything).  ev[] (optional, 6 events) are recorded at the
 // stage boundaries the reference times in Match (ADCensusStereo.cpp:81-129).
-int enqueue_pipeline(adc_engine* e, Lane& ln, int nS, int last_stage, cudaEvent_t* ev) {
+// `set` >= 0 (async_refine, full pipeline only): the wave works on that buffer set and everything after WTA goes to ln.st_ref;
+// *result_stream receives the stream on which the final map becomes available.
+int enqueue_pipeline(adc_engine* e, Lane& ln, int nS, int last_stage, cudaEvent_t* ev, int set = -1,
+                     cudaStream_t* result_stream = nullptr) {
     const AdcParams& P = e->P;
-    const AdcWave w = wave_view(e, ln, nS);
+    const AdcWave w = wave_view(e, ln, nS, set);
     cudaStream_t st = ln.st;
+    if (result_stream) *result_stream = st;
     unsigned long long* L = &e->launches;
     const size_t mapN = (size_t)nS * P.dm.N;
     float* A = w.volA;
@@ -279,6 +339,12 @@ int enqueue_pipeline(adc_engine* e, Lane& ln, int nS, int last_stage, cudaEvent_
     if (adc_launch_wta(P, w, A, st, L)) return fail(ADC_ERR_UNSUPPORTED, "WTA launch failed");
     if (ev) CK(cudaEventRecord(ev[4], st));
     if (stop(ADC_STAGE_WTA)) return ADC_OK;
+    if (set >= 0) {   // hand the wave over to the refinement stream; ln.st is free for the next wave's volumes
+        CK(cudaEventRecord(ln.rs[set].ev_vol, st));
+        CK(cudaStreamWaitEvent(ln.st_ref, ln.rs[set].ev_vol, 0));
+        st = ln.st_ref;
+        if (result_stream) *result_stream = st;
+    }
 
     // ---- stage 5: multi-step refinement (multistep_refiner.cpp:60-87)
     if (e->opt.do_lr_check) {
@@ -322,6 +388,7 @@ bool is_pinned(const void* p) {
 }
 
 int drain_lane(adc_engine* e, Lane& ln) {
+    if (ln.st_ref && ln.drain_n == 0) { CK(cudaStreamSynchronize(ln.st_ref)); return ADC_OK; }
     if (ln.drain_n == 0) return ADC_OK;
     CK(cudaEventSynchronize(ln.ev_done));
     const size_t N = (size_t)e->P.dm.N;
@@ -346,24 +413,30 @@ int run_batch(adc_engine* e, int n, SrcKind kind, const uint8_t* const* lp, cons
     for (int wv = 0; wv < n_waves; wv++) {
         Lane& ln = e->lanes[wv % nl];
         const int first = wv * S, nS = std::min(S, n - first);
-        // ---- inputs -> ln.w.bgr  ([S][2][IMG])
+        // async_refine: this wave's buffer set (the depth-discontinuity step reads the cost volume during refinement, which
+        // the next wave would already be overwriting: that option keeps the single-stream schedule)
+        const int set = (ln.st_ref && !e->opt.do_discontinuity_adjustment) ? (int)(ln.wave_no++ & 1) : -1;
+        const AdcWave& io = set >= 0 ? ln.rs[set].w : ln.w;   // where the images go in and the map comes out
+        if (set >= 0) CK(cudaStreamWaitEvent(ln.st, ln.rs[set].ev_free, 0));   // the set's previous wave has left it
+        ln.last_set = set;
+        // ---- inputs -> io.bgr  ([S][2][IMG])
         if (kind == SRC_DEVICE_STRIDED) {
-            CK(cudaMemcpy2DAsync(ln.w.bgr, 2 * IMG, ls + (size_t)first * IMG, IMG, IMG, nS, cudaMemcpyDeviceToDevice, ln.st));
-            CK(cudaMemcpy2DAsync(ln.w.bgr + IMG, 2 * IMG, rs + (size_t)first * IMG, IMG, IMG, nS, cudaMemcpyDeviceToDevice, ln.st));
+            CK(cudaMemcpy2DAsync(io.bgr, 2 * IMG, ls + (size_t)first * IMG, IMG, IMG, nS, cudaMemcpyDeviceToDevice, ln.st));
+            CK(cudaMemcpy2DAsync(io.bgr + IMG, 2 * IMG, rs + (size_t)first * IMG, IMG, IMG, nS, cudaMemcpyDeviceToDevice, ln.st));
         } else if (pinned) {
             if (kind == SRC_HOST_STRIDED) {
-                CK(cudaMemcpy2DAsync(ln.w.bgr, 2 * IMG, ls + (size_t)first * IMG, IMG, IMG, nS, cudaMemcpyHostToDevice, ln.st));
-                CK(cudaMemcpy2DAsync(ln.w.bgr + IMG, 2 * IMG, rs + (size_t)first * IMG, IMG, IMG, nS, cudaMemcpyHostToDevice, ln.st));
+                CK(cudaMemcpy2DAsync(io.bgr, 2 * IMG, ls + (size_t)first * IMG, IMG, IMG, nS, cudaMemcpyHostToDevice, ln.st));
+                CK(cudaMemcpy2DAsync(io.bgr + IMG, 2 * IMG, rs + (size_t)first * IMG, IMG, IMG, nS, cudaMemcpyHostToDevice, ln.st));
             } else {
                 for (int i = 0; i < nS; i++) {
-                    CK(cudaMemcpyAsync(ln.w.bgr + (size_t)i * 2 * IMG, lp[first + i], IMG, cudaMemcpyHostToDevice, ln.st));
-                    CK(cudaMemcpyAsync(ln.w.bgr + (size_t)i * 2 * IMG + IMG, rp[first + i], IMG, cudaMemcpyHostToDevice, ln.st));
+                    CK(cudaMemcpyAsync(io.bgr + (size_t)i * 2 * IMG, lp[first + i], IMG, cudaMemcpyHostToDevice, ln.st));
+                    CK(cudaMemcpyAsync(io.bgr + (size_t)i * 2 * IMG + IMG, rp[first + i], IMG, cudaMemcpyHostToDevice, ln.st));
                 }
             }
         } else {
             // pageable caller memory: finish the lane's previous wave (copy-out), then stage through pinned memory
-            int rc = drain_lane(e, ln);
-            if (rc) return rc;
+            int rcd = drain_lane(e, ln);
+            if (rcd) return rcd;
             CK(cudaEventSynchronize(ln.ev_in_free));
             for (int i = 0; i < nS; i++) {
                 const uint8_t* l = kind == SRC_HOST_PTRS ? lp[first + i] : ls + (size_t)(first + i) * IMG;
@@ -371,29 +444,31 @@ int run_batch(adc_engine* e, int n, SrcKind kind, const uint8_t* const* lp, cons
                 memcpy(ln.pin_in + (size_t)i * 2 * IMG, l, IMG);
                 memcpy(ln.pin_in + (size_t)i * 2 * IMG + IMG, r, IMG);
             }
-            CK(cudaMemcpyAsync(ln.w.bgr, ln.pin_in, (size_t)nS * 2 * IMG, cudaMemcpyHostToDevice, ln.st));
+            CK(cudaMemcpyAsync(io.bgr, ln.pin_in, (size_t)nS * 2 * IMG, cudaMemcpyHostToDevice, ln.st));
             CK(cudaEventRecord(ln.ev_in_free, ln.st));
         }
         // ---- compute
-        int rc = enqueue_pipeline(e, ln, nS, ADC_STAGE_MEDIAN, nullptr);
+        cudaStream_t rst = ln.st;   // stream on which the map becomes available
+        int rc = enqueue_pipeline(e, ln, nS, ADC_STAGE_MEDIAN, nullptr, set, &rst);
         if (rc) return rc;
         // ---- outputs
         if (kind == SRC_DEVICE_STRIDED) {
-            CK(cudaMemcpyAsync(ds + (size_t)first * N, ln.w.disp_l, (size_t)nS * N * sizeof(float), cudaMemcpyDeviceToDevice, ln.st));
+            CK(cudaMemcpyAsync(ds + (size_t)first * N, io.disp_l, (size_t)nS * N * sizeof(float), cudaMemcpyDeviceToDevice, rst));
         } else if (pinned) {
             if (kind == SRC_HOST_STRIDED) {
-                CK(cudaMemcpyAsync(ds + (size_t)first * N, ln.w.disp_l, (size_t)nS * N * sizeof(float), cudaMemcpyDeviceToHost, ln.st));
+                CK(cudaMemcpyAsync(ds + (size_t)first * N, io.disp_l, (size_t)nS * N * sizeof(float), cudaMemcpyDeviceToHost, rst));
             } else {
                 for (int i = 0; i < nS; i++)
-                    CK(cudaMemcpyAsync(dp[first + i], ln.w.disp_l + (size_t)i * N, N * sizeof(float), cudaMemcpyDeviceToHost, ln.st));
+                    CK(cudaMemcpyAsync(dp[first + i], io.disp_l + (size_t)i * N, N * sizeof(float), cudaMemcpyDeviceToHost, rst));
             }
         } else {
-            CK(cudaMemcpyAsync(ln.pin_out, ln.w.disp_l, (size_t)nS * N * sizeof(float), cudaMemcpyDeviceToHost, ln.st));
+            CK(cudaMemcpyAsync(ln.pin_out, io.disp_l, (size_t)nS * N * sizeof(float), cudaMemcpyDeviceToHost, rst));
             ln.drain_n = nS; ln.drain_first = first;
             ln.drain_ptrs = kind == SRC_HOST_PTRS ? dp : nullptr;
             ln.drain_base = ds;
         }
-        CK(cudaEventRecord(ln.ev_done, ln.st));
+        if (set >= 0) CK(cudaEventRecord(ln.rs[set].ev_free, rst));   // the wave has left its buffer set
+        CK(cudaEventRecord(ln.ev_done, rst));
     }
     // join: the caller's stream waits for every lane -- unless the engine is in pipelined mode, where consecutive
     // batch calls flow into each other (a lane starts the next call's wave while other lanes still finish the
@@ -437,6 +512,12 @@ void adc_destroy(adc_engine* e) {
         if (ln.pin_out) cudaFreeHost(ln.pin_out);
         if (ln.ev_done) cudaEventDestroy(ln.ev_done);
         if (ln.ev_in_free) cudaEventDestroy(ln.ev_in_free);
+        for (auto& r : ln.rs) {
+            if (r.arena) cudaFree(r.arena);
+            if (r.ev_vol) cudaEventDestroy(r.ev_vol);
+            if (r.ev_free) cudaEventDestroy(r.ev_free);
+        }
+        if (ln.st_ref) cudaStreamDestroy(ln.st_ref);
         if (ln.st) cudaStreamDestroy(ln.st);
     }
     if (e->d_lut_ad) cudaFree(e->d_lut_ad);
@@ -480,13 +561,15 @@ int adc_create(int32_t width, int32_t height, const adc_option* opt, const adc_c
     int nl = e->cfg.lanes > 0 ? e->cfg.lanes : 4;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "cudaMemGetInfo failed"));
+    bool async_refine = e->cfg.async_refine != 0;
+    if (const char* m = getenv("ADC_ASYNC_REFINE")) async_refine = atoi(m) != 0;
     while (true) {
-        const size_t need = carve_lane(nullptr, e->P.dm, S, nullptr) * nl;
+        const size_t need = (carve_lane(nullptr, e->P.dm, S, nullptr) + (async_refine ? 2 * carve_refset(nullptr, e->P.dm, S, nullptr) : 0)) * nl;
         if (need < free_b * 8 / 10) break;
         if (nl > 1) nl--; else if (S > 1) S--; else return bail(fail(ADC_ERR_NOMEM, "adc_create: one pair does not fit in device memory"));
     }
     e->S = S;
-    e->cfg.wave_pairs = S; e->cfg.lanes = nl;
+    e->cfg.wave_pairs = S; e->cfg.lanes = nl; e->cfg.async_refine = async_refine ? 1 : 0;
 
     int rc = upload_tables(e);
     if (rc) return bail(rc);
@@ -503,6 +586,17 @@ int adc_create(int32_t width, int32_t height, const adc_option* opt, const adc_c
         if (cudaMalloc(&ln.arena, bytes) != cudaSuccess) { cudaGetLastError(); return bail(fail(ADC_ERR_NOMEM, "device arena of %zu bytes", bytes)); }
         carve_lane(ln.arena, e->P.dm, S, &ln.w);
         if (cudaMemsetAsync(ln.arena, 0, bytes, ln.st) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "memset failed"));
+        if (async_refine) {
+            if (cudaStreamCreateWithFlags(&ln.st_ref, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "stream create failed"));
+            const size_t rbytes = carve_refset(nullptr, e->P.dm, S, nullptr);
+            for (auto& r : ln.rs) {
+                if (cudaEventCreateWithFlags(&r.ev_vol, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&r.ev_free, cudaEventDisableTiming) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "event create failed"));
+                if (cudaMalloc(&r.arena, rbytes) != cudaSuccess) { cudaGetLastError(); return bail(fail(ADC_ERR_NOMEM, "refinement buffer set of %zu bytes", rbytes)); }
+                carve_refset(r.arena, e->P.dm, S, &r.w);
+                if (cudaMemsetAsync(r.arena, 0, rbytes, ln.st) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "memset failed"));
+            }
+        }
         if (cudaHostAlloc((void**)&ln.pin_in, (size_t)S * 2 * N * 3, cudaHostAllocDefault) != cudaSuccess ||
             cudaHostAlloc((void**)&ln.pin_out, (size_t)S * N * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {
             cudaGetLastError();
@@ -594,7 +688,10 @@ void adc_host_free(void* p) { if (p) cudaFreeHost(p); }
 int adc_synchronize(adc_engine* e) {
     if (!e) return fail(ADC_ERR_ARG, "adc_synchronize: engine is NULL");
     CK(cudaSetDevice(e->cfg.device));
-    for (auto& ln : e->lanes) CK(cudaStreamSynchronize(ln.st));
+    for (auto& ln : e->lanes) {
+        CK(cudaStreamSynchronize(ln.st));
+        if (ln.st_ref) CK(cudaStreamSynchronize(ln.st_ref));
+    }
     CK(cudaStreamSynchronize(e->main_st));
     return ADC_OK;
 }
@@ -688,10 +785,11 @@ int adc_profile_kernel(adc_engine* e, int32_t kernel_id, int32_t reps, float* av
     CK(cudaSetDevice(e->cfg.device));
     Lane& ln = e->lanes[0];
     const AdcParams& P = e->P;
-    const AdcWave w = wave_view(e, ln, e->S);
+    const AdcWave w = wave_view(e, ln, e->S, ln.last_set);   // (an async_refine lane keeps arms etc. in its buffer sets)
     const double V = (double)P.dm.N * P.dm.D * 4.0, N = (double)P.dm.N;
     double bytes = 0;
     CK(cudaStreamSynchronize(ln.st));
+    if (ln.st_ref) CK(cudaStreamSynchronize(ln.st_ref));
     cudaEvent_t e0 = e->ev_stage[0], e1 = e->ev_stage[1];
     for (int r = -1; r < reps; r++) {   // r = -1: warm-up launch
         if (r == 0) CK(cudaEventRecord(e0, ln.st));

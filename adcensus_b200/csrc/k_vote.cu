@@ -547,7 +547,7 @@ bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st,
     k_vote_transpose<<<tgrid, 256, 0, st>>>(dm, w.arms, w.vote_atbT);
     dim3 sgrid(64, w.S);
     k_vote_slots<<<sgrid, 256, 0, st>>>(dm, w.vlist, w.counters, w.vote_state, w.vote_pslotT, w.sup_h);
-    unsigned* hist = reinterpret_cast<unsigned*>(w.volB);
+    unsigned* hist = w.vote_hist;
     int gx = (148 * 8 + w.S - 1) / w.S;
     if (gx < 1) gx = 1;
     dim3 igrid(gx, w.S);

@@ -47,8 +47,8 @@ assert ctypes.sizeof(ADCensusOption) == 60
 
 class _Config(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int32), ("wave_pairs", ctypes.c_int32), ("lanes", ctypes.c_int32),
-                ("force_generic", ctypes.c_int32), ("use_graphs", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 11)]
+                ("force_generic", ctypes.c_int32), ("use_graphs", ctypes.c_int32), ("async_refine", ctypes.c_int32),
+                ("reserved", ctypes.c_int32 * 10)]
 
 
 class AdcError(RuntimeError):
@@ -123,12 +123,12 @@ class Engine:
     """Thin object wrapper over adc_create/.../adc_destroy."""
 
     def __init__(self, width: int, height: int, option: ADCensusOption | None = None, device: int = 0,
-                 wave_pairs: int = 0, lanes: int = 0):
+                 wave_pairs: int = 0, lanes: int = 0, async_refine: bool = False):
         self._L = load_library()
         self.width, self.height = int(width), int(height)
         self.option = option or ADCensusOption()
         self.D = self.option.max_disparity - self.option.min_disparity
-        cfg = _Config(device=device, wave_pairs=wave_pairs, lanes=lanes)
+        cfg = _Config(device=device, wave_pairs=wave_pairs, lanes=lanes, async_refine=1 if async_refine else 0)
         h = ctypes.c_void_p()
         _check(self._L.adc_create(self.width, self.height, ctypes.byref(self.option), ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h

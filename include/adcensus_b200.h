@@ -61,7 +61,9 @@ typedef struct adc_config {
     int32_t lanes;           /* concurrent waves in flight, one stream each (default: auto) */
     int32_t force_generic;   /* 1: always use the unfused per-pass kernels (the path the debug taps see) */
     int32_t use_graphs;      /* 1: replay each wave as a CUDA graph */
-    int32_t reserved[11];
+    int32_t async_refine;    /* 1: a lane runs the refinement stage of wave k on a second stream, on its own buffer set,
+                                while its first stream already streams the volumes of wave k+1 (experimental, off) */
+    int32_t reserved[10];
 } adc_config;
 
 /* stands in for: ADCensusOption::ADCensusOption() defaults (adcensus_types.h:67-74) */
