@@ -293,3 +293,29 @@ def test_pipelined_batches(cone):
         assert (got.cpu().numpy().view(np.uint32) == want.view(np.uint32)[None]).all()
     eng.set_pipelined(False)
     eng.close()
+
+
+def test_async_refine_lanes(cone):
+    """adc_config.async_refine (experimental): a lane's refinement stage on a second stream with its own buffer set while
+    the first stream streams the next wave's volumes.  Same bits as the plain schedule, over several waves per lane."""
+    import torch
+    left, right = cone
+    h, w, _ = left.shape
+    plain = _engine(w, h, T.default_option(), wave_pairs=4, lanes=2)
+    want = [plain.match(left, right), plain.match(right, left)]
+    plain.close()
+    eng = _engine(w, h, T.default_option(), wave_pairs=4, lanes=2, async_refine=True)
+    n = 24
+    L = np.stack([left if i % 2 == 0 else right for i in range(n)])
+    R = np.stack([right if i % 2 == 0 else left for i in range(n)])
+    dl, dr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    dd = torch.zeros((n, h, w), dtype=torch.float32, device="cuda")
+    for _ in range(2):
+        eng.match_batch_device(n, dl.data_ptr(), dr.data_ptr(), dd.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    out = dd.cpu().numpy()
+    for i in range(n):
+        assert out[i].tobytes() == want[i % 2].tobytes(), f"pair {i}"
+    # the synchronous single-pair entry still works on such an engine (lane buffers, both streams idle)
+    assert eng.match(left, right).tobytes() == want[0].tobytes()
+    eng.close()
