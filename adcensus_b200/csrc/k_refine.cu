@@ -277,7 +277,6 @@ k_region_voting_global(AdcParams P, const uchar4* __restrict__ arms, float* disp
     int n_list[2] = {__ldcg(cnt + 0), __ldcg(cnt + 1)};
     int rounds_total = 0, evals = 0;
     int* hist = s_hist[wid];
-    const int grp = lane >> 3, sub = lane & 7;
 
     // nothing stamped, nothing evaluated: stamp(0) >= last_eval(0) makes the first round evaluate everyone
     for (int i = gtid; i < tw * th; i += n_gthreads) __stcg(tiles + i, 0);
@@ -620,7 +619,6 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
 
 void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
     // disp_l = committed state (OLD), disp_t = working copy (NEW); both hold the post-outlier map here
-    const int reach = P.L1 > 0 ? P.L1 : 0;
     static int mode = -1;   // development switch: 4 = incremental histograms (k_vote.cu, default), 1 = byte-state pull kernel,
                             // 2 = float state via L2, 3 = float state via L1
     if (mode < 0) { const char* m = getenv("ADC_VOTE_MODE"); mode = m ? atoi(m) : 4; }
