@@ -135,7 +135,10 @@ dist.destroy_process_group()
 def test_two_rank_scatter_gather_gloo(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
-    port = str(29600 + os.getpid() % 300)
+    import socket
+    with socket.socket() as sk:          # a port the kernel says is free right now (a fixed one can be in TIME_WAIT)
+        sk.bind(("127.0.0.1", 0))
+        port = str(sk.getsockname()[1])
     procs = []
     for r in range(2):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", ADC_ROOT=str(ROOT), ADC_PORT=port)
