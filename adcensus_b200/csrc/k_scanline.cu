@@ -171,7 +171,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-template <int K, int LPS, bool FULL>   // FULL: D == LPS*K, every lane's K values are real disparities (no padding logic)
+template <int K, int LPS, bool FULL, bool CT = false>   // FULL: D == LPS*K, every lane's K values are real disparities (no padding logic)
+                                                        // CT (experimental, ADC_SO_CT=1, needs FULL): strides and chunk counts as compile-time constants
 __global__ void __launch_bounds__(SO_WARPS * 32)
 k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
            const unsigned* __restrict__ rec, int sx, int sy) {
@@ -185,7 +186,7 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
     const int pair = blockIdx.y;
     const int n_lines = sx ? dm.H : dm.W, n_steps = sx ? dm.W : dm.H;
     const bool live = line < n_lines;            // dead groups run along (uniform control flow) but move no data
-    const int W = dm.W, D = dm.D, Dp = dm.Dp;
+    const int W = dm.W, D = (FULL && CT) ? K * LPS : dm.D, Dp = (FULL && CT) ? K * LPS : dm.Dp;   // (FULL: D == Dp == K*LPS)
     const int pstep = sx + sy * W;               // signed pixel stride along the path
     const int nrec = so_rec_words(Dp);
     const int cost_chunks = Dp >> 2, rec_chunks = nrec >> 2;      // 16-byte chunks per step
@@ -289,7 +290,7 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
     cp_async_wait<0>();
 }
 
-template <int K, int LPS, bool FULL>
+template <int K, int LPS, bool FULL, bool CT = false>
 static int launch_scanline_kf(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
                              cudaStream_t st) {
     constexpr int LPW = 32 / LPS;
@@ -298,17 +299,20 @@ static int launch_scanline_kf(const AdcParams& P, const AdcWave& w, const float*
     const size_t smem = (size_t)SO_WARPS * LPW * SO_PF * slot_bytes;
     static bool attr_done[64] = {};
     if (adc_first_time_on_device(attr_done)) {
-        cudaFuncSetAttribute(k_scanline<K, LPS, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_scanline<K, LPS, FULL, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     }
     const int lines_per_block = SO_WARPS * LPW;
     dim3 grid((n_lines + lines_per_block - 1) / lines_per_block, w.S);
-    k_scanline<K, LPS, FULL><<<grid, SO_WARPS * 32, smem, st>>>(P, src, dst, w.so_rec, sx, sy);
+    k_scanline<K, LPS, FULL, CT><<<grid, SO_WARPS * 32, smem, st>>>(P, src, dst, w.so_rec, sx, sy);
     return 0;
 }
 
 template <int K, int LPS>
 static int launch_scanline_k(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
                              cudaStream_t st) {
+    static int ct = -1;   // ADC_SO_CT=1: compile-time strides for the exact-fit instantiation (not validated on a GPU yet)
+    if (ct < 0) { const char* m = getenv("ADC_SO_CT"); ct = m ? atoi(m) : 0; }
+    if (P.dm.D == K * LPS && P.dm.Dp == K * LPS && ct && K == 8 && LPS == 8) return launch_scanline_kf<K, LPS, true, (K == 8 && LPS == 8)>(P, w, src, dst, sx, sy, st);
     if (P.dm.D == K * LPS) return launch_scanline_kf<K, LPS, true>(P, w, src, dst, sx, sy, st);
     return launch_scanline_kf<K, LPS, false>(P, w, src, dst, sx, sy, st);
 }
