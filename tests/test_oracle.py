@@ -68,7 +68,12 @@ def test_oracle_vs_live_reference(case):
         ref.step()
         for tap in T.STAGE_TAPS[st]:
             a, b = orc.tap(tap), ref.tap(tap)
-            assert a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"{st}/{tap}"
+            if tap == "DISP_R" and opt.min_disparity > 0:
+                # right pixels x >= W - dmin have no candidate column at all: the reference then runs its parabola on an
+                # uninitialised cost_local[] (ADCensusStereo.cpp:271-300) -- whatever the heap held; the
+                # restatement writes the integer 0 there.  Undefined in the reference, so not compared.
+                a, b = a[:, :w - opt.min_disparity], b[:, :w - opt.min_disparity]
+            assert a.shape == b.shape and np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8)), f"{st}/{tap}"
 
 
 def test_gray_exhaustive():
