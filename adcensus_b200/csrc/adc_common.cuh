@@ -35,6 +35,7 @@ struct AdcParams {
     int irv_ts; float irv_th;
     float lr_thres;
     int max_search;              // max(|dmax|,|dmin|)
+    int dbg;                     // adc_config.debug_flags (test hooks, ADC_DBG_* in adcensus_b200.h)
 };
 
 __device__ __forceinline__ int adc_colour_dist(uchar3 a, uchar3 b) {
@@ -57,13 +58,20 @@ __device__ __forceinline__ float adc_key2f(unsigned k) {
 }
 
 // Function attributes and __device__ / __constant__ symbols exist once per device: one-time set-up is keyed by the
-// current device (one process may own engines on several GPUs).  Racing threads at worst repeat the same set-up.
-inline bool adc_first_time_on_device(bool (&done)[64]) {
+// current device (one process may own engines on several GPUs, driven from several threads: the flags are atomics, and
+// a thread that loses the race may run the kernel before the winner's attribute call has returned -- so every caller
+// that finds the flag unset performs the (idempotent) set-up itself, and the flag is only published afterwards).
+#include <atomic>
+struct AdcOnce { std::atomic<int> done[64]; };
+inline bool adc_once_needed(AdcOnce& o) {
     int dev = 0;
     cudaGetDevice(&dev);
-    if (done[dev & 63]) return false;
-    done[dev & 63] = true;
-    return true;
+    return o.done[dev & 63].load(std::memory_order_acquire) == 0;
+}
+inline void adc_once_done(AdcOnce& o) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    o.done[dev & 63].store(1, std::memory_order_release);
 }
 
 // ---- launchers (defined in the k_*.cu files; all asynchronous on `st`) -------------------------
@@ -75,6 +83,7 @@ struct AdcWave {            // device pointers of one wave (S pairs)
     unsigned long long* census; // [S][2][N]
     float* volA; float* volB;
     uchar4* arms;
+    unsigned* arm_rec;      // [S][window records of both axes] which of a group's four outputs takes which tap (k_aggregate.cu)
     uint16_t* sup_h; uint16_t* sup_v;
     uint8_t* dmap;          // [S][4][N]: 0 = left-horizontal, 1 = left-vertical, 2 = right-horizontal, 3 = right-vertical
     float* disp_l; float* disp_r; float* disp_t;
@@ -95,11 +104,10 @@ struct AdcWave {            // device pointers of one wave (S pairs)
     int* vote_pslotT;       // [S][W][H]  region voting: histogram slot of a pending pixel, -1 otherwise (transposed)
     uint8_t* vote_val;      // [S][N]     region voting: current vote per slot (255 = none)
     uint8_t* vote_dirtyb;   // [S][N]     region voting: slot's histogram changed since its last derive
-    uint8_t* vote_dead;     // [S][N]     (unused)
     int* vote_state;        // [S][N]     region voting: disparity index of a valid pixel, -1 invalid, -(slot+2) pending
     int* vote_deg;          // [S][N]     region voting: adjacency list lengths / fill cursors per slot
     int* vote_off;          // [S][N+1]   region voting: adjacency list offsets (CSR by target slot)
-    unsigned* vote_hist;    // [S][vol_stride] region voting: histograms + forward lists + adjacency (= volB unless the lane refines asynchronously)
+    unsigned* vote_hist;    // [S][vol_stride] region voting: histograms + forward lists + adjacency (= volB, idle after the last scanline pass)
     const float* lut_ad;    // [766]  (1 - exp(-(s/3)/lambda_ad)) + 1, host libm expf
     const float* lut_cen;   // [64]   exp(-h/lambda_census)
     const double* ray_sin; const double* ray_cos; // [16] host libm sin/cos of the accumulated angles
@@ -114,6 +122,12 @@ void adc_launch_arms(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsi
 // optionally divided by the support count `sup` (second pass of an iteration)
 void adc_launch_arm_sum(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int dir,
                         const uint16_t* sup, cudaStream_t st, unsigned long long* launches);
+// two consecutive passes along the same axis (second pass of an iteration, divided by `sup_mid`, then the first pass of the
+// next iteration) with the intermediate kept in shared memory; false = not applicable for these parameters, nothing launched
+bool adc_arm_sum2_available(const AdcParams& P);
+bool adc_launch_arm_sum2(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int dir,
+                         const uint16_t* sup_mid, cudaStream_t st, unsigned long long* launches);
+size_t adc_arm_rec_bytes(const AdcDims& dm, int L1);   // window records of one pair
 void adc_launch_so_bitrows(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
 size_t adc_so_rec_bytes(const AdcDims& dm);
 size_t adc_so_bitrow_bytes(const AdcDims& dm);

@@ -57,13 +57,6 @@ struct Lane {
     AdcWave w{};                       // device pointers, capacity S pairs
     uint8_t* pin_in = nullptr;         // [S][2][N*3] pinned staging (pageable callers only)
     float* pin_out = nullptr;          // [S][N]
-    // async_refine (experimental): the refinement stage of a wave runs on st_ref on one of two buffer sets while st already
-    // streams the volumes of the lane's next wave.  ev_vol: the wave's volume stage (up to WTA) is done; ev_free: the wave has
-    // left the set (its result copy-out included).
-    cudaStream_t st_ref = nullptr;
-    struct RefSet { void* arena = nullptr; AdcWave w{}; cudaEvent_t ev_vol = nullptr, ev_free = nullptr; } rs[2];
-    unsigned long long wave_no = 0;
-    int last_set = -1;
     // pending copy-out of a staged wave (pageable callers)
     int drain_n = 0;
     float* const* drain_ptrs = nullptr;
@@ -87,6 +80,7 @@ struct adc_engine {
     double* d_rays = nullptr;  // [32]: sin[16], cos[16]
     short2* d_ray_off = nullptr;  // [16][max_search] integer ray offsets, when verified exact for this image size
     bool pipelined = false;            // adc_set_pipelined: batch calls do not join the caller's stream themselves
+    bool agg_fused = false;            // same-axis aggregation passes of neighbouring iterations run as one kernel (k_arm_sum2)
     unsigned long long launches = 0;
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t ev_stage[8] = {};
@@ -112,7 +106,7 @@ struct Carver {
 };
 
 // Carves (or, with base == nullptr, just sizes) one lane's arena.
-size_t carve_lane(void* base, const AdcDims& dm, int S, AdcWave* w) {
+size_t carve_lane(void* base, const AdcDims& dm, int L1, int S, AdcWave* w) {
     Carver c(base);
     const size_t N = (size_t)dm.N;
     AdcWave t{};
@@ -123,6 +117,7 @@ size_t carve_lane(void* base, const AdcDims& dm, int S, AdcWave* w) {
     t.bgrx = c.take<unsigned>((size_t)S * 2 * N);
     t.census = c.take<unsigned long long>((size_t)S * 2 * N);
     t.arms = c.take<uchar4>((size_t)S * N);
+    t.arm_rec = c.take<unsigned>((size_t)S * adc_arm_rec_bytes(dm, L1) / 4);
     t.sup_h = c.take<uint16_t>((size_t)S * N);
     t.sup_v = c.take<uint16_t>((size_t)S * N);
     t.dmap = c.take<uint8_t>((size_t)S * 4 * N);
@@ -141,7 +136,6 @@ size_t carve_lane(void* base, const AdcDims& dm, int S, AdcWave* w) {
     t.vote_pslotT = c.take<int>((size_t)S * N);
     t.vote_val = c.take<uint8_t>((size_t)S * N);
     t.vote_dirtyb = c.take<uint8_t>((size_t)S * N);
-    t.vote_dead = c.take<uint8_t>((size_t)S * N);
     t.vote_state = c.take<int>((size_t)S * N);
     t.vote_deg = c.take<int>((size_t)S * N);
     t.vote_off = c.take<int>((size_t)S * (N + 1));
@@ -152,44 +146,6 @@ size_t carve_lane(void* base, const AdcDims& dm, int S, AdcWave* w) {
     t.tile_stamp = c.take<int>((size_t)S * ((dm.W + 15) / 16) * ((dm.H + 15) / 16));
     t.last_eval = c.take<int>((size_t)S * N);
     t.vote_hist = reinterpret_cast<unsigned*>(t.volB);   // idle after the last scanline pass
-    if (w) *w = t;
-    return c.off;
-}
-
-// Carves (or sizes) one refinement buffer set of an async_refine lane: everything the kernels after WTA read or write,
-// plus what the volume stage produces for them (packed images, arms, support counts, the two disparity maps).
-size_t carve_refset(void* base, const AdcDims& dm, int S, AdcWave* w) {
-    Carver c(base);
-    const size_t N = (size_t)dm.N;
-    AdcWave t{};
-    t.bgr = c.take<uint8_t>((size_t)S * 2 * N * 3);
-    t.bgrx = c.take<unsigned>((size_t)S * 2 * N);
-    t.arms = c.take<uchar4>((size_t)S * N);
-    t.sup_h = c.take<uint16_t>((size_t)S * N);
-    t.sup_v = c.take<uint16_t>((size_t)S * N);
-    t.disp_l = c.take<float>((size_t)S * N);
-    t.disp_r = c.take<float>((size_t)S * N);
-    t.disp_t = c.take<float>((size_t)S * N);
-    t.label = c.take<uint8_t>((size_t)S * N);
-    t.flag = c.take<uint8_t>((size_t)S * N);
-    t.pend = c.take<int>((size_t)S * 2 * N);
-    t.vlist = c.take<int>((size_t)S * 2 * N);
-    t.counters = c.take<int>((size_t)S * ADC_CNT);
-    t.vote_dq = c.take<uint8_t>((size_t)S * 2 * N);
-    t.vote_alr = c.take<uchar2>((size_t)S * N);
-    t.vote_dirty = c.take<int2>((size_t)S * N);
-    t.vote_atbT = c.take<uchar2>((size_t)S * N);
-    t.vote_pslotT = c.take<int>((size_t)S * N);
-    t.vote_val = c.take<uint8_t>((size_t)S * N);
-    t.vote_dirtyb = c.take<uint8_t>((size_t)S * N);
-    t.vote_dead = c.take<uint8_t>((size_t)S * N);
-    t.vote_state = c.take<int>((size_t)S * N);
-    t.vote_deg = c.take<int>((size_t)S * N);
-    t.vote_off = c.take<int>((size_t)S * (N + 1));
-    t.rowcnt = c.take<int>((size_t)S * 2 * dm.H);
-    t.tile_stamp = c.take<int>((size_t)S * ((dm.W + 15) / 16) * ((dm.H + 15) / 16));
-    t.last_eval = c.take<int>((size_t)S * N);
-    t.vote_hist = c.take<unsigned>((size_t)S * dm.vol_stride);
     if (w) *w = t;
     return c.off;
 }
@@ -213,6 +169,7 @@ void build_params(adc_engine* e) {
     P.irv_ts = o.irv_ts; P.irv_th = o.irv_th;
     P.lr_thres = o.lrcheck_thres;
     P.max_search = std::max(abs(o.max_disparity), abs(o.min_disparity));  // multistep_refiner.cpp:236
+    P.dbg = e->cfg.debug_flags;
 }
 
 int upload_tables(adc_engine* e) {
@@ -246,7 +203,7 @@ int upload_tables(adc_engine* e) {
     // that equals y + lround(m*sin) unless a rounding of the double sum (or a half-way case) intervenes;
     // check every (ray, m, coordinate) the image can produce and only then let the kernel use the table.
     const int L = e->P.max_search;
-    if (L > 1 && L < 4096) {
+    if (L > 1 && L < 4096 && !(e->cfg.debug_flags & ADC_DBG_NO_RAY_TABLE)) {
         std::vector<short2> off((size_t)16 * L);
         bool exact = true;
         for (int s = 0; s < 16 && exact; s++)
@@ -264,18 +221,8 @@ int upload_tables(adc_engine* e) {
     return ADC_OK;
 }
 
-AdcWave wave_view(const adc_engine* e, const Lane& ln, int nS, int set = -1) {
+AdcWave wave_view(const adc_engine* e, const Lane& ln, int nS) {
     AdcWave w = ln.w;
-    if (set >= 0) {   // async_refine: the wave's refinement buffers come from the set, the volume-stage buffers from the lane
-        const AdcWave& r = ln.rs[set].w;
-        w.bgr = r.bgr; w.bgrx = r.bgrx; w.arms = r.arms; w.sup_h = r.sup_h; w.sup_v = r.sup_v;
-        w.disp_l = r.disp_l; w.disp_r = r.disp_r; w.disp_t = r.disp_t; w.label = r.label; w.flag = r.flag;
-        w.pend = r.pend; w.vlist = r.vlist; w.counters = r.counters; w.vote_dq = r.vote_dq; w.vote_alr = r.vote_alr;
-        w.vote_dirty = r.vote_dirty; w.vote_atbT = r.vote_atbT; w.vote_pslotT = r.vote_pslotT; w.vote_val = r.vote_val;
-        w.vote_dirtyb = r.vote_dirtyb; w.vote_dead = r.vote_dead; w.vote_state = r.vote_state; w.vote_deg = r.vote_deg;
-        w.vote_off = r.vote_off; w.rowcnt = r.rowcnt; w.tile_stamp = r.tile_stamp; w.last_eval = r.last_eval;
-        w.vote_hist = r.vote_hist;
-    }
     w.S = nS;
     w.lut_ad = e->d_lut_ad;
     w.lut_cen = e->d_lut_cen;
@@ -288,38 +235,63 @@ AdcWave wave_view(const adc_engine* e, const Lane& ln, int nS, int set = -1) {
 // Enqueues the whole pipeline for the nS pairs whose images already sit in ln.w.bgr.  Stops after
 // `last_stage` (ADC_STAGE_MEDIAN = everything).  ev[] (optional, 6 events) are recorded at the
 // stage boundaries the reference times in Match (ADCensusStereo.cpp:81-129).
-// `set` >= 0 (async_refine, full pipeline only): the wave works on that buffer set and everything after WTA goes to ln.st_ref;
-// *result_stream receives the stream on which the final map becomes available.
-int enqueue_pipeline(adc_engine* e, Lane& ln, int nS, int last_stage, cudaEvent_t* ev, int set = -1,
-                     cudaStream_t* result_stream = nullptr) {
+int enqueue_pipeline(adc_engine* e, Lane& ln, int nS, int last_stage, cudaEvent_t* ev) {
     const AdcParams& P = e->P;
-    const AdcWave w = wave_view(e, ln, nS, set);
+    const AdcWave w = wave_view(e, ln, nS);
     cudaStream_t st = ln.st;
-    if (result_stream) *result_stream = st;
     unsigned long long* L = &e->launches;
     const size_t mapN = (size_t)nS * P.dm.N;
+    // The two volumes play the reference's cost_init_ / cost_aggr_.  The aggregation leaves its result in volA either way:
+    //   eight single passes:   cost -> A | H: A->B, V/: B->A | V: A->B, H/: B->A | ...                          (8 x 2 = 16 volume transfers)
+    //   same-axis passes fused (second pass of iteration k + first pass of iteration k+1 in one kernel):
+    //                          cost -> B | H: B->A | V/ V: A->B | H/ H: B->A | V/ V: A->B | H/: B->A           (5 x 2 = 10 volume transfers)
+    // A run that has to stop between iterations (debug taps AGG1..AGG3) takes the single passes.
+    const bool fused = e->agg_fused && !(last_stage >= ADC_STAGE_AGG1 && last_stage <= ADC_STAGE_AGG3);
     float* A = w.volA;
     float* B = w.volB;
-    e->dbg_init = A;
-    e->dbg_aggr = A;
+    float* C0 = fused ? B : A;          // where the cost volume is written
+    e->dbg_init = C0;
+    e->dbg_aggr = C0;
     auto stop = [&](int stage) { e->dbg_stage = stage; return stage >= last_stage; };
+    // launch errors surface where they happen: a stage boundary reports the first failed launch since the previous one
+    auto launched = [&](const char* what) -> int {
+        const cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return fail(ADC_ERR_CUDA, "%s: kernel launch failed: %s", what, cudaGetErrorString(err));
+        return ADC_OK;
+    };
+    int rc;
 
     // ---- stage 1: cost (cost_computor.cpp:123-137)
     adc_launch_gray_census(P, w, st, L);
-    adc_launch_cost(P, w, A, st, L);
+    adc_launch_cost(P, w, C0, st, L);
+    if ((rc = launched("cost volume"))) return rc;
     if (ev) CK(cudaEventRecord(ev[1], st));
     if (stop(ADC_STAGE_COST)) return ADC_OK;
 
-    // ---- stage 2: arms, support counts, 4 aggregation iterations (cross_aggregator.cpp:89-118)
+    // ---- stage 2: arms, support counts, window records, 4 aggregation iterations (cross_aggregator.cpp:89-118)
     adc_launch_arms(P, w, st, L);
+    if ((rc = launched("cross arms"))) return rc;
     if (stop(ADC_STAGE_ARMS)) return ADC_OK;
-    for (int it = 0; it < 4; it++) {
-        const bool hfirst = (it % 2) == 0;  // H,V | V,H | H,V | V,H  (:102,116)
-        adc_launch_arm_sum(P, w, A, B, hfirst ? 0 : 1, nullptr, st, L);
-        adc_launch_arm_sum(P, w, B, A, hfirst ? 1 : 0, hfirst ? w.sup_h : w.sup_v, st, L);
-        if (stop(ADC_STAGE_AGG1 + it)) return ADC_OK;
+    if (fused) {
+        adc_launch_arm_sum(P, w, B, A, 0, nullptr, st, L);                       // it 0: H
+        if (!adc_launch_arm_sum2(P, w, A, B, 1, w.sup_h, st, L) ||               // it 0: V /   + it 1: V
+            !adc_launch_arm_sum2(P, w, B, A, 0, w.sup_v, st, L) ||               // it 1: H /   + it 2: H
+            !adc_launch_arm_sum2(P, w, A, B, 1, w.sup_h, st, L))                 // it 2: V /   + it 3: V
+            return fail(ADC_ERR_UNSUPPORTED, "fused aggregation pass not applicable");
+        adc_launch_arm_sum(P, w, B, A, 0, w.sup_v, st, L);                       // it 3: H /
+        e->dbg_aggr = A;
+        e->dbg_stage = ADC_STAGE_AGG4;
+    } else {
+        for (int it = 0; it < 4; it++) {
+            const bool hfirst = (it % 2) == 0;  // H,V | V,H | H,V | V,H  (:102,116)
+            adc_launch_arm_sum(P, w, A, B, hfirst ? 0 : 1, nullptr, st, L);
+            adc_launch_arm_sum(P, w, B, A, hfirst ? 1 : 0, hfirst ? w.sup_h : w.sup_v, st, L);
+            if (stop(ADC_STAGE_AGG1 + it)) return launched("aggregation");
+        }
     }
+    if ((rc = launched("aggregation"))) return rc;
     if (ev) CK(cudaEventRecord(ev[2], st));
+    if (last_stage <= ADC_STAGE_AGG4) return ADC_OK;
 
     // ---- stage 3: scanline optimisation, 4 chained passes (scanline_optimizer.cpp:54-60)
     adc_launch_diffmaps(P, w, st, L);
@@ -331,20 +303,16 @@ int enqueue_pipeline(adc_engine* e, Lane& ln, int nS, int last_stage, cudaEvent_
         if (adc_launch_scanline(P, w, src, dst, dirs[ps][0], dirs[ps][1], st, L))
             return fail(ADC_ERR_UNSUPPORTED, "disparity range %d exceeds the scanline kernel's limit of 256", P.dm.D);
         if (ps % 2 == 0) e->dbg_init = B; else e->dbg_aggr = A;
-        if (stop(ADC_STAGE_SO1 + ps)) return ADC_OK;
+        if (stop(ADC_STAGE_SO1 + ps)) return launched("scanline optimisation");
     }
+    if ((rc = launched("scanline optimisation"))) return rc;
     if (ev) CK(cudaEventRecord(ev[3], st));
 
     // ---- stage 4: left + right disparity (ADCensusStereo.cpp:108-109)
     if (adc_launch_wta(P, w, A, st, L)) return fail(ADC_ERR_UNSUPPORTED, "WTA launch failed");
+    if ((rc = launched("winner-takes-all"))) return rc;
     if (ev) CK(cudaEventRecord(ev[4], st));
     if (stop(ADC_STAGE_WTA)) return ADC_OK;
-    if (set >= 0) {   // hand the wave over to the refinement stream; ln.st is free for the next wave's volumes
-        CK(cudaEventRecord(ln.rs[set].ev_vol, st));
-        CK(cudaStreamWaitEvent(ln.st_ref, ln.rs[set].ev_vol, 0));
-        st = ln.st_ref;
-        if (result_stream) *result_stream = st;
-    }
 
     // ---- stage 5: multi-step refinement (multistep_refiner.cpp:60-87)
     if (e->opt.do_lr_check) {
@@ -354,31 +322,31 @@ int enqueue_pipeline(adc_engine* e, Lane& ln, int nS, int last_stage, cudaEvent_
         CK(cudaMemsetAsync(w.label, 0, mapN, st));
         CK(cudaMemcpyAsync(w.disp_t, w.disp_l, mapN * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    if (stop(ADC_STAGE_OUTLIER)) return ADC_OK;
+    if (stop(ADC_STAGE_OUTLIER)) return launched("outlier detection");
     if (e->opt.do_filling) {  // gates voting AND interpolation (ADCensusStereo.cpp:183)
         CK(cudaMemsetAsync(w.counters, 0, (size_t)nS * ADC_CNT * sizeof(int), st));
         adc_launch_build_lists(P, w, st, L);
         adc_launch_voting(P, w, st, L);
+        if ((rc = launched("region voting"))) return rc;
         if (stop(ADC_STAGE_VOTE)) return ADC_OK;
         for (int k = 0; k < 2; k++) {
             adc_launch_interp_list(P, w, k, st, L);
             CK(cudaMemcpyAsync(w.disp_l, w.disp_t, mapN * sizeof(float), cudaMemcpyDeviceToDevice, st));
         }
-        if (stop(ADC_STAGE_INTERP)) return ADC_OK;
+        if (stop(ADC_STAGE_INTERP)) return launched("interpolation");
     } else if (last_stage <= ADC_STAGE_INTERP) {
         e->dbg_stage = last_stage;
-        return ADC_OK;
+        return launched("refinement");
     }
     if (e->opt.do_discontinuity_adjustment) adc_launch_discontinuity(P, w, A, st, L);
-    if (stop(ADC_STAGE_DISC)) return ADC_OK;
+    if (stop(ADC_STAGE_DISC)) return launched("discontinuity adjustment");
     // median: disp_l -> disp_t, then back so that disp_l always holds the current map
     if (adc_launch_median(P, w, w.disp_l, w.disp_t, st, L))
-        return fail(ADC_ERR_UNSUPPORTED, "image height %d exceeds the median kernel's limit of 2048 rows", P.dm.H);
+        return fail(ADC_ERR_UNSUPPORTED, "image height %d exceeds the median kernel's limit", P.dm.H);
     CK(cudaMemcpyAsync(w.disp_l, w.disp_t, mapN * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (ev) CK(cudaEventRecord(ev[5], st));
     e->dbg_stage = ADC_STAGE_MEDIAN;
-    CK(cudaGetLastError());
-    return ADC_OK;
+    return launched("refinement");
 }
 
 bool is_pinned(const void* p) {
@@ -388,7 +356,6 @@ bool is_pinned(const void* p) {
 }
 
 int drain_lane(adc_engine* e, Lane& ln) {
-    if (ln.st_ref && ln.drain_n == 0) { CK(cudaStreamSynchronize(ln.st_ref)); return ADC_OK; }
     if (ln.drain_n == 0) return ADC_OK;
     CK(cudaEventSynchronize(ln.ev_done));
     const size_t N = (size_t)e->P.dm.N;
@@ -403,8 +370,11 @@ int drain_lane(adc_engine* e, Lane& ln) {
 enum SrcKind { SRC_HOST_PTRS, SRC_HOST_STRIDED, SRC_DEVICE_STRIDED };
 
 // Common batch driver.  `user` = stream to fork from / join to.
+// `force_join`: the call is one of the synchronous entry points, whose results must be complete on return whatever the
+// engine's pipelined setting (adc_set_pipelined only changes the asynchronous entry points).
 int run_batch(adc_engine* e, int n, SrcKind kind, const uint8_t* const* lp, const uint8_t* const* rp,
-              float* const* dp, const uint8_t* ls, const uint8_t* rs, float* ds, cudaStream_t user, bool pinned) {
+              float* const* dp, const uint8_t* ls, const uint8_t* rs, float* ds, cudaStream_t user, bool pinned,
+              bool force_join = false) {
     const size_t N = (size_t)e->P.dm.N, IMG = N * 3;
     const int S = e->S, nl = (int)e->lanes.size();
     CK(cudaEventRecord(e->ev_fork, user));
@@ -413,12 +383,7 @@ int run_batch(adc_engine* e, int n, SrcKind kind, const uint8_t* const* lp, cons
     for (int wv = 0; wv < n_waves; wv++) {
         Lane& ln = e->lanes[wv % nl];
         const int first = wv * S, nS = std::min(S, n - first);
-        // async_refine: this wave's buffer set (the depth-discontinuity step reads the cost volume during refinement, which
-        // the next wave would already be overwriting: that option keeps the single-stream schedule)
-        const int set = (ln.st_ref && !e->opt.do_discontinuity_adjustment) ? (int)(ln.wave_no++ & 1) : -1;
-        const AdcWave& io = set >= 0 ? ln.rs[set].w : ln.w;   // where the images go in and the map comes out
-        if (set >= 0) CK(cudaStreamWaitEvent(ln.st, ln.rs[set].ev_free, 0));   // the set's previous wave has left it
-        ln.last_set = set;
+        const AdcWave& io = ln.w;   // where the images go in and the map comes out
         // ---- inputs -> io.bgr  ([S][2][IMG])
         if (kind == SRC_DEVICE_STRIDED) {
             CK(cudaMemcpy2DAsync(io.bgr, 2 * IMG, ls + (size_t)first * IMG, IMG, IMG, nS, cudaMemcpyDeviceToDevice, ln.st));
@@ -449,7 +414,7 @@ int run_batch(adc_engine* e, int n, SrcKind kind, const uint8_t* const* lp, cons
         }
         // ---- compute
         cudaStream_t rst = ln.st;   // stream on which the map becomes available
-        int rc = enqueue_pipeline(e, ln, nS, ADC_STAGE_MEDIAN, nullptr, set, &rst);
+        int rc = enqueue_pipeline(e, ln, nS, ADC_STAGE_MEDIAN, nullptr);
         if (rc) return rc;
         // ---- outputs
         if (kind == SRC_DEVICE_STRIDED) {
@@ -467,13 +432,12 @@ int run_batch(adc_engine* e, int n, SrcKind kind, const uint8_t* const* lp, cons
             ln.drain_ptrs = kind == SRC_HOST_PTRS ? dp : nullptr;
             ln.drain_base = ds;
         }
-        if (set >= 0) CK(cudaEventRecord(ln.rs[set].ev_free, rst));   // the wave has left its buffer set
         CK(cudaEventRecord(ln.ev_done, rst));
     }
     // join: the caller's stream waits for every lane -- unless the engine is in pipelined mode, where consecutive
     // batch calls flow into each other (a lane starts the next call's wave while other lanes still finish the
     // previous call's) and the caller joins once with adc_join
-    if (!e->pipelined || (!pinned && kind != SRC_DEVICE_STRIDED))
+    if (!e->pipelined || force_join || (!pinned && kind != SRC_DEVICE_STRIDED))
         for (int li = 0; li < std::min(nl, n_waves); li++) CK(cudaStreamWaitEvent(user, e->lanes[li].ev_done, 0));
     if (!pinned && kind != SRC_DEVICE_STRIDED)
         for (auto& ln : e->lanes) { int rc = drain_lane(e, ln); if (rc) return rc; }
@@ -512,12 +476,6 @@ void adc_destroy(adc_engine* e) {
         if (ln.pin_out) cudaFreeHost(ln.pin_out);
         if (ln.ev_done) cudaEventDestroy(ln.ev_done);
         if (ln.ev_in_free) cudaEventDestroy(ln.ev_in_free);
-        for (auto& r : ln.rs) {
-            if (r.arena) cudaFree(r.arena);
-            if (r.ev_vol) cudaEventDestroy(r.ev_vol);
-            if (r.ev_free) cudaEventDestroy(r.ev_free);
-        }
-        if (ln.st_ref) cudaStreamDestroy(ln.st_ref);
         if (ln.st) cudaStreamDestroy(ln.st);
     }
     if (e->d_lut_ad) cudaFree(e->d_lut_ad);
@@ -537,9 +495,16 @@ int adc_create(int32_t width, int32_t height, const adc_option* opt, const adc_c
     if (width <= 0 || height <= 0) return fail(ADC_ERR_ARG, "adc_create: non-positive image size %dx%d", width, height);
     if (opt->max_disparity - opt->min_disparity <= 0)
         return fail(ADC_ERR_ARG, "adc_create: empty disparity range [%d,%d)", opt->min_disparity, opt->max_disparity);
-    if ((long long)width * height > (1ll << 28)) return fail(ADC_ERR_UNSUPPORTED, "adc_create: image too large");
-    if (opt->max_disparity - opt->min_disparity > 256)
-        return fail(ADC_ERR_UNSUPPORTED, "adc_create: disparity range %d > 256 is not supported", opt->max_disparity - opt->min_disparity);
+    // Limits of the kernels (the reference has none; INTEGRATION.md lists them).  They are checked HERE, so that a caller
+    // never sees Initialize() succeed and Match() fail for a size: whatever adc_create accepts, adc_match runs.
+    const int drange = opt->max_disparity - opt->min_disparity;
+    if ((long long)width * height > (1ll << 28)) return fail(ADC_ERR_UNSUPPORTED, "adc_create: image too large (more than 2^28 pixels)");
+    if (drange > ADC_MAX_DISPARITY_RANGE)
+        return fail(ADC_ERR_UNSUPPORTED, "adc_create: disparity range %d > %d is not supported (scanline kernel: 8 disparities per lane)", drange, ADC_MAX_DISPARITY_RANGE);
+    if (height > ADC_MAX_HEIGHT)
+        return fail(ADC_ERR_UNSUPPORTED, "adc_create: image height %d > %d is not supported (in-place median: one CTA per image)", height, ADC_MAX_HEIGHT);
+    if (width > ADC_MAX_WIDTH || width + drange > ADC_MAX_WIDTH)
+        return fail(ADC_ERR_UNSUPPORTED, "adc_create: image width %d (+ disparity range %d) > %d is not supported (cost kernel stages a right-image row in shared memory)", width, drange, ADC_MAX_WIDTH);
 
     adc_engine* e = new adc_engine();
     e->W = width; e->H = height; e->opt = *opt;
@@ -561,15 +526,14 @@ int adc_create(int32_t width, int32_t height, const adc_option* opt, const adc_c
     int nl = e->cfg.lanes > 0 ? e->cfg.lanes : 4;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "cudaMemGetInfo failed"));
-    bool async_refine = e->cfg.async_refine != 0;
-    if (const char* m = getenv("ADC_ASYNC_REFINE")) async_refine = atoi(m) != 0;
     while (true) {
-        const size_t need = (carve_lane(nullptr, e->P.dm, S, nullptr) + (async_refine ? 2 * carve_refset(nullptr, e->P.dm, S, nullptr) : 0)) * nl;
+        const size_t need = carve_lane(nullptr, e->P.dm, e->P.L1, S, nullptr) * nl;
         if (need < free_b * 8 / 10) break;
         if (nl > 1) nl--; else if (S > 1) S--; else return bail(fail(ADC_ERR_NOMEM, "adc_create: one pair does not fit in device memory"));
     }
     e->S = S;
-    e->cfg.wave_pairs = S; e->cfg.lanes = nl; e->cfg.async_refine = async_refine ? 1 : 0;
+    e->cfg.wave_pairs = S; e->cfg.lanes = nl;
+    e->agg_fused = adc_arm_sum2_available(e->P) && !(e->cfg.debug_flags & ADC_DBG_UNFUSED_AGG);
 
     int rc = upload_tables(e);
     if (rc) return bail(rc);
@@ -582,21 +546,10 @@ int adc_create(int32_t width, int32_t height, const adc_option* opt, const adc_c
         if (cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "stream create failed"));
         if (cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "event create failed"));
         if (cudaEventCreateWithFlags(&ln.ev_in_free, cudaEventDisableTiming) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "event create failed"));
-        const size_t bytes = carve_lane(nullptr, e->P.dm, S, nullptr);
+        const size_t bytes = carve_lane(nullptr, e->P.dm, e->P.L1, S, nullptr);
         if (cudaMalloc(&ln.arena, bytes) != cudaSuccess) { cudaGetLastError(); return bail(fail(ADC_ERR_NOMEM, "device arena of %zu bytes", bytes)); }
-        carve_lane(ln.arena, e->P.dm, S, &ln.w);
+        carve_lane(ln.arena, e->P.dm, e->P.L1, S, &ln.w);
         if (cudaMemsetAsync(ln.arena, 0, bytes, ln.st) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "memset failed"));
-        if (async_refine) {
-            if (cudaStreamCreateWithFlags(&ln.st_ref, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "stream create failed"));
-            const size_t rbytes = carve_refset(nullptr, e->P.dm, S, nullptr);
-            for (auto& r : ln.rs) {
-                if (cudaEventCreateWithFlags(&r.ev_vol, cudaEventDisableTiming) != cudaSuccess ||
-                    cudaEventCreateWithFlags(&r.ev_free, cudaEventDisableTiming) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "event create failed"));
-                if (cudaMalloc(&r.arena, rbytes) != cudaSuccess) { cudaGetLastError(); return bail(fail(ADC_ERR_NOMEM, "refinement buffer set of %zu bytes", rbytes)); }
-                carve_refset(r.arena, e->P.dm, S, &r.w);
-                if (cudaMemsetAsync(r.arena, 0, rbytes, ln.st) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "memset failed"));
-            }
-        }
         if (cudaHostAlloc((void**)&ln.pin_in, (size_t)S * 2 * N * 3, cudaHostAllocDefault) != cudaSuccess ||
             cudaHostAlloc((void**)&ln.pin_out, (size_t)S * N * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {
             cudaGetLastError();
@@ -631,6 +584,15 @@ int adc_match(adc_engine* e, const uint8_t* img_left, const uint8_t* img_right, 
     return ADC_OK;
 }
 
+int adc_get_right_disparity(adc_engine* e, float* disp_right) {
+    if (!e || !disp_right) return fail(ADC_ERR_ARG, "adc_get_right_disparity: bad arguments");
+    CK(cudaSetDevice(e->cfg.device));
+    Lane& ln = e->lanes[0];
+    CK(cudaStreamSynchronize(ln.st));
+    CK(cudaMemcpy(disp_right, ln.w.disp_r, (size_t)e->P.dm.N * sizeof(float), cudaMemcpyDeviceToHost));
+    return ADC_OK;
+}
+
 int adc_match_batch(adc_engine* e, int32_t n, const uint8_t* const* img_left, const uint8_t* const* img_right,
                     float* const* disp_left) {
     if (!e) return fail(ADC_ERR_ARG, "adc_match_batch: engine is NULL");
@@ -642,7 +604,7 @@ int adc_match_batch(adc_engine* e, int32_t n, const uint8_t* const* img_left, co
     }
     CK(cudaSetDevice(e->cfg.device));
     for (int i = 0; i < n && pinned; i++) pinned = is_pinned(img_left[i]) && is_pinned(img_right[i]) && is_pinned(disp_left[i]);
-    int rc = run_batch(e, n, SRC_HOST_PTRS, img_left, img_right, disp_left, nullptr, nullptr, nullptr, e->main_st, pinned);
+    int rc = run_batch(e, n, SRC_HOST_PTRS, img_left, img_right, disp_left, nullptr, nullptr, nullptr, e->main_st, pinned, true);
     if (rc) return rc;
     CK(cudaStreamSynchronize(e->main_st));
     return ADC_OK;
@@ -654,7 +616,7 @@ int adc_match_batch_strided(adc_engine* e, int32_t n, const uint8_t* left, const
     if (n == 0) return ADC_OK;
     CK(cudaSetDevice(e->cfg.device));
     const bool pinned = is_pinned(left) && is_pinned(right) && is_pinned(disp);
-    int rc = run_batch(e, n, SRC_HOST_STRIDED, nullptr, nullptr, nullptr, left, right, disp, e->main_st, pinned);
+    int rc = run_batch(e, n, SRC_HOST_STRIDED, nullptr, nullptr, nullptr, left, right, disp, e->main_st, pinned, true);
     if (rc) return rc;
     CK(cudaStreamSynchronize(e->main_st));
     return ADC_OK;
@@ -690,7 +652,6 @@ int adc_synchronize(adc_engine* e) {
     CK(cudaSetDevice(e->cfg.device));
     for (auto& ln : e->lanes) {
         CK(cudaStreamSynchronize(ln.st));
-        if (ln.st_ref) CK(cudaStreamSynchronize(ln.st_ref));
     }
     CK(cudaStreamSynchronize(e->main_st));
     return ADC_OK;
@@ -785,11 +746,10 @@ int adc_profile_kernel(adc_engine* e, int32_t kernel_id, int32_t reps, float* av
     CK(cudaSetDevice(e->cfg.device));
     Lane& ln = e->lanes[0];
     const AdcParams& P = e->P;
-    const AdcWave w = wave_view(e, ln, e->S, ln.last_set);   // (an async_refine lane keeps arms etc. in its buffer sets)
+    const AdcWave w = wave_view(e, ln, e->S);
     const double V = (double)P.dm.N * P.dm.D * 4.0, N = (double)P.dm.N;
     double bytes = 0;
     CK(cudaStreamSynchronize(ln.st));
-    if (ln.st_ref) CK(cudaStreamSynchronize(ln.st_ref));
     cudaEvent_t e0 = e->ev_stage[0], e1 = e->ev_stage[1];
     for (int r = -1; r < reps; r++) {   // r = -1: warm-up launch
         if (r == 0) CK(cudaEventRecord(e0, ln.st));
@@ -800,6 +760,9 @@ int adc_profile_kernel(adc_engine* e, int32_t kernel_id, int32_t reps, float* av
             case 3: if (adc_launch_scanline(P, w, w.volA, w.volB, 1, 0, ln.st, &e->launches)) return fail(ADC_ERR_UNSUPPORTED, "scanline"); bytes = 2 * V + 6 * N; break;
             case 4: if (adc_launch_scanline(P, w, w.volA, w.volB, 0, 1, ln.st, &e->launches)) return fail(ADC_ERR_UNSUPPORTED, "scanline"); bytes = 2 * V + 6 * N; break;
             case 5: if (adc_launch_wta(P, w, w.volA, ln.st, &e->launches)) return fail(ADC_ERR_UNSUPPORTED, "wta"); bytes = V + 8 * N; break;
+            case 6: if (!adc_launch_arm_sum2(P, w, w.volA, w.volB, 1, w.sup_h, ln.st, &e->launches)) return fail(ADC_ERR_UNSUPPORTED, "fused vertical arm sums not applicable"); bytes = 2 * V + 6 * N; break;
+            case 7: if (!adc_launch_arm_sum2(P, w, w.volA, w.volB, 0, w.sup_v, ln.st, &e->launches)) return fail(ADC_ERR_UNSUPPORTED, "fused horizontal arm sums not applicable"); bytes = 2 * V + 6 * N; break;
+            case 8: adc_launch_arm_sum(P, w, w.volA, w.volB, 0, w.sup_v, ln.st, &e->launches); bytes = 2 * V + 6 * N; break;
             default: return fail(ADC_ERR_ARG, "adc_profile_kernel: unknown kernel id %d", kernel_id);
         }
     }

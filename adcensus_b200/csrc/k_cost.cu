@@ -154,9 +154,10 @@ void adc_launch_cost(const AdcParams& P, const AdcWave& w, float* vol, cudaStrea
     const int threads = ppc * Q;
     const int span = P.dm.W + P.dm.D - 1, sq = (span + 3) / 4 + 1;
     const size_t smem = (size_t)(64 * 32 + 766 * CV_AD_REP) * 4 + (size_t)4 * sq * 12;
-    static bool attr_done[64] = {};
-    if (adc_first_time_on_device(attr_done)) {
+    static AdcOnce attr_once;
+    if (adc_once_needed(attr_once)) {
         cudaFuncSetAttribute(k_cost_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        adc_once_done(attr_once);
     }
     dim3 grid(P.dm.H, w.S);
     k_cost_volume<<<grid, threads, smem, st>>>(P.dm, ppc, w.bgrx, w.census, vol, w.lut_ad, w.lut_cen);

@@ -617,42 +617,26 @@ k_region_voting_bytes(AdcParams P, const uchar4* __restrict__ arms, const uchar2
     }
 }
 
+// Three kernels, chosen by the parameters alone (each has its parity cases in tests/test_gpu_parity.py):
+//   D <= 254 and L1 <= 127   incremental histograms, k_vote.cu (every BASELINE configuration)
+//   D <= 254, L1 > 127       byte-state pull kernel (a cross region may hold more than 65535 pixels)
+//   D = 255, 256             float-state pull kernel (the byte state codes a disparity index in one byte)
 void adc_launch_voting(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
     // disp_l = committed state (OLD), disp_t = working copy (NEW); both hold the post-outlier map here
-    static int mode = -1;   // development switch: 4 = incremental histograms (k_vote.cu, default), 1 = byte-state pull kernel,
-                            // 2 = float state via L2, 3 = float state via L1
-    if (mode < 0) { const char* m = getenv("ADC_VOTE_MODE"); mode = m ? atoi(m) : 4; }
     dim3 egrid((P.dm.N + 255) / 256, w.S);
-    if (mode == 4 && P.dm.D <= 254) {
+    if (P.dm.D <= 254) {
         launch_active_lists(P, w, st, launches);
         k_vote_encode<<<egrid, 256, 0, st>>>(P.dm, w.disp_l, w.arms, w.vote_dq, w.vote_alr, w.vote_state);
         ++*launches;
-        if (adc_launch_vote_push(P, w, st, launches)) {
-            adc_launch_build_lists(P, w, st, launches);   // outlier lists = every listed pixel that is still invalid
-            return;
+        if (!adc_launch_vote_push(P, w, st, launches)) {
+            k_region_voting_bytes<<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.vote_alr, w.disp_l, w.disp_t, w.vote_dq,
+                                                                          w.label, w.vlist, w.counters, w.tile_stamp, w.last_eval);
+            ++*launches;
         }
-        mode = 1;   // not applicable for these parameters: the pull kernel below (lists and byte state are ready)
-        k_region_voting_bytes<<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.vote_alr, w.disp_l, w.disp_t, w.vote_dq,
-                                                                      w.label, w.vlist, w.counters, w.tile_stamp, w.last_eval);
-        ++*launches;
-        adc_launch_build_lists(P, w, st, launches);
-        mode = 4;
-        return;
-    }
-    if (mode == 1 && P.dm.D <= 254) {
-        launch_active_lists(P, w, st, launches);
-        k_vote_encode<<<egrid, 256, 0, st>>>(P.dm, w.disp_l, w.arms, w.vote_dq, w.vote_alr, nullptr);
-        k_region_voting_bytes<<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.vote_alr, w.disp_l, w.disp_t, w.vote_dq,
-                                                                      w.label, w.vlist, w.counters, w.tile_stamp, w.last_eval);
-        *launches += 2;
         adc_launch_build_lists(P, w, st, launches);   // outlier lists = every listed pixel that is still invalid
     } else {
-        if (mode != 3)
-            k_region_voting_global<false><<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.disp_l, w.disp_t, w.label, w.pend,
-                                                                                   w.counters, w.tile_stamp, w.last_eval);
-        else
-            k_region_voting_global<true><<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.disp_l, w.disp_t, w.label, w.pend,
-                                                                                  w.counters, w.tile_stamp, w.last_eval);
+        k_region_voting_global<false><<<w.S * RV_CLUSTER, RV_THREADS, 0, st>>>(P, w.arms, w.disp_l, w.disp_t, w.label, w.pend,
+                                                                               w.counters, w.tile_stamp, w.last_eval);
         ++*launches;
     }
 }
@@ -932,14 +916,13 @@ __device__ __forceinline__ float median9(float v[9]) {
     return v[4];
 }
 
-#define MED_PF 8   // wavefront steps between issuing a load and using it
 
 __device__ __forceinline__ void med_cp4(float* smem_dst, const float* gmem_src) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src) : "memory");
 }
 
-template <int MED_ROWS>   // rows per thread: 1 for H <= 1024, 2 up to 2048
+template <int MED_ROWS, int MED_PF>   // rows per thread (1 for H <= 1024, 2 up to 2048, 4 up to 4096); wavefront steps between issuing a load and using it
 __global__ void __launch_bounds__(MED_THREADS)
 k_median_wavefront(AdcDims dm, const float* __restrict__ in, float* __restrict__ out) {
     extern __shared__ float med_smem[];
@@ -1034,17 +1017,21 @@ k_median_wavefront(AdcDims dm, const float* __restrict__ in, float* __restrict__
 
 int adc_launch_median(const AdcParams& P, const AdcWave& w, const float* in, float* out, cudaStream_t st,
                       unsigned long long* launches) {
-    if (P.dm.H > MED_THREADS * 2) return 1;
-    const int rows = P.dm.H <= MED_THREADS ? 1 : 2;
+    if (P.dm.H > MED_THREADS * 4) return 1;        // (adc_create rejects such images: ADC_MAX_HEIGHT)
+    const int rows = P.dm.H <= MED_THREADS ? 1 : (P.dm.H <= 2 * MED_THREADS ? 2 : 4);
+    const int pf = rows == 4 ? 4 : 8;
     const int threads = std::min(MED_THREADS, ((P.dm.H + rows - 1) / rows + 31) / 32 * 32);
-    const size_t smem = ((size_t)P.dm.H * 4 + (size_t)threads * rows * MED_PF * 2) * sizeof(float);
-    static bool attr_done[64] = {};
-    if (adc_first_time_on_device(attr_done)) {
-        cudaFuncSetAttribute(k_median_wavefront<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_median_wavefront<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const size_t smem = ((size_t)P.dm.H * 4 + (size_t)threads * rows * pf * 2) * sizeof(float);
+    static AdcOnce attr_once;
+    if (adc_once_needed(attr_once)) {
+        cudaFuncSetAttribute(k_median_wavefront<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_median_wavefront<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_median_wavefront<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        adc_once_done(attr_once);
     }
-    if (rows == 1) k_median_wavefront<1><<<w.S, threads, smem, st>>>(P.dm, in, out);
-    else           k_median_wavefront<2><<<w.S, threads, smem, st>>>(P.dm, in, out);
+    if (rows == 1)      k_median_wavefront<1, 8><<<w.S, threads, smem, st>>>(P.dm, in, out);
+    else if (rows == 2) k_median_wavefront<2, 8><<<w.S, threads, smem, st>>>(P.dm, in, out);
+    else                k_median_wavefront<4, 4><<<w.S, threads, smem, st>>>(P.dm, in, out);
     ++*launches;
     return 0;
 }

@@ -6,7 +6,7 @@
 #include "jet_lut.h"
 
 __constant__ unsigned char c_jet[256 * 3];
-static bool g_jet_uploaded[64] = {};   // per device
+static AdcOnce g_jet_uploaded;   // per device
 
 // min / max of |d| over the valid pixels; starting values float(width) / -float(width) as in main.cpp:151,185
 __global__ void k_render_init(unsigned* mm, int width) {
@@ -69,7 +69,10 @@ k_render_cloud(int W, const int* __restrict__ list, const int* __restrict__ coun
 
 int adc_launch_render(const AdcDims& dm, const float* d_disp, unsigned* d_mm, uint8_t* d_gray, uint8_t* d_jet, float* d_mm_out,
                       cudaStream_t st, unsigned long long* launches) {
-    if (adc_first_time_on_device(g_jet_uploaded) && cudaMemcpyToSymbol(c_jet, ADC_JET_LUT, sizeof(ADC_JET_LUT)) != cudaSuccess) return 1;
+    if (adc_once_needed(g_jet_uploaded)) {
+        if (cudaMemcpyToSymbol(c_jet, ADC_JET_LUT, sizeof(ADC_JET_LUT)) != cudaSuccess) return 1;
+        adc_once_done(g_jet_uploaded);
+    }
     k_render_init<<<1, 1, 0, st>>>(d_mm, dm.W);
     k_render_minmax<<<148, 256, 0, st>>>(dm.N, d_disp, d_mm);
     k_render_gray_jet<<<(dm.N + 255) / 256, 256, 0, st>>>(dm.N, d_disp, d_mm, d_gray, d_jet, d_mm_out);

@@ -297,9 +297,10 @@ static int launch_scanline_kf(const AdcParams& P, const AdcWave& w, const float*
     const int n_lines = sx ? P.dm.H : P.dm.W;
     const int slot_bytes = (P.dm.Dp + so_rec_words(P.dm.Dp)) * 4;
     const size_t smem = (size_t)SO_WARPS * LPW * SO_PF * slot_bytes;
-    static bool attr_done[64] = {};
-    if (adc_first_time_on_device(attr_done)) {
+    static AdcOnce attr_once;
+    if (adc_once_needed(attr_once)) {
         cudaFuncSetAttribute(k_scanline<K, LPS, FULL, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        adc_once_done(attr_once);
     }
     const int lines_per_block = SO_WARPS * LPW;
     dim3 grid((n_lines + lines_per_block - 1) / lines_per_block, w.S);

@@ -33,7 +33,6 @@
 // that are almost entirely invalid), the pair falls back to enumerating the inverse region of every change
 // on the fly from transposed arm tables (push_enum below).
 #include "adc_common.cuh"
-#include <stdlib.h>
 
 #define VP_THREADS 1024
 #define VP_WARPS (VP_THREADS / 32)
@@ -97,44 +96,50 @@ __device__ __forceinline__ void vote_scan_region(int p, int W, const uchar4* __r
     const uchar4 a = __ldg(A + p);
     const int top = a.z, rows = top + (int)a.w + 1;
     const int rbase = (y - top) * W + x;
-    unsigned ar[3];
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        const int ri = lane + 32 * j;
-        uchar2 v = make_uchar2(0, 0);
-        if (ri < rows) v = __ldg(ALR + rbase + ri * W);
-        ar[j] = (unsigned)v.x | ((unsigned)v.y << 8);
-    }
     const int grp = lane / LPR, sub = lane % LPR;
-    for (int r0 = 0; r0 < rows; r0 += 4 * RPT) {
-        int v0[4], v1[4], cl[4], ch[4], ro[4];
+    // the horizontal arms are cached 96 rows at a time (lane r holds rows r, r+32, r+64 of the chunk); a region has
+    // up to 2*L1+1 <= 511 rows, the default L1 = 34 gives at most 69: one chunk
+    for (int rb = 0; rb < rows; rb += 96) {
+        const int rows_c = min(rows - rb, 96);
+        const int cbase = rbase + rb * W;
+        unsigned ar[3];
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const int ri = r0 + RPT * t + grp;
-            unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
-            if (rows > 32) {
-                const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31), a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
-                a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
+        for (int j = 0; j < 3; j++) {
+            const int ri = lane + 32 * j;
+            uchar2 v = make_uchar2(0, 0);
+            if (ri < rows_c) v = __ldg(ALR + cbase + ri * W);
+            ar[j] = (unsigned)v.x | ((unsigned)v.y << 8);
+        }
+        for (int r0 = 0; r0 < rows_c; r0 += 4 * RPT) {
+            int v0[4], v1[4], cl[4], ch[4], ro[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int ri = r0 + RPT * t + grp;
+                unsigned a2 = __shfl_sync(0xffffffffu, ar[0], ri & 31);
+                if (rows_c > 32) {
+                    const unsigned a2b = __shfl_sync(0xffffffffu, ar[1], ri & 31), a2c = __shfl_sync(0xffffffffu, ar[2], ri & 31);
+                    a2 = ri < 32 ? a2 : (ri < 64 ? a2b : a2c);
+                }
+                ro[t] = cbase + ri * W;
+                cl[t] = -(int)(a2 & 255u) + sub;
+                ch[t] = ri < rows_c ? (int)(a2 >> 8) : -0x10000;     // rows past the chunk: empty segment
+                v0[t] = cl[t] <= ch[t] ? __ldg(VS + ro[t] + cl[t]) : -1;
+                v1[t] = cl[t] + LPR <= ch[t] ? __ldg(VS + ro[t] + cl[t] + LPR) : -1;
             }
-            ro[t] = rbase + ri * W;
-            cl[t] = -(int)(a2 & 255u) + sub;
-            ch[t] = ri < rows ? (int)(a2 >> 8) : -0x10000;     // rows past the region: empty segment
-            v0[t] = cl[t] <= ch[t] ? __ldg(VS + ro[t] + cl[t]) : -1;
-            v1[t] = cl[t] + LPR <= ch[t] ? __ldg(VS + ro[t] + cl[t] + LPR) : -1;
-        }
-        int more = 0;
+            int more = 0;
 #pragma unroll
-        for (int t = 0; t < 4; t++) more = max(more, (ch[t] - cl[t]) / LPR);
-        more = __reduce_max_sync(0xffffffffu, more);          // LPR-column chunks the widest row of the trip needs, minus one
+            for (int t = 0; t < 4; t++) more = max(more, (ch[t] - cl[t]) / LPR);
+            more = __reduce_max_sync(0xffffffffu, more);          // LPR-column chunks the widest row of the trip needs, minus one
 #pragma unroll
-        for (int t = 0; t < 4; t++) visit(v0[t]);
-        if (more >= 1) {
+            for (int t = 0; t < 4; t++) visit(v0[t]);
+            if (more >= 1) {
 #pragma unroll
-            for (int t = 0; t < 4; t++) visit(v1[t]);
-        }
-        for (int k = 2; k <= more; k++) {                     // wider rows
+                for (int t = 0; t < 4; t++) visit(v1[t]);
+            }
+            for (int k = 2; k <= more; k++) {                     // wider rows
 #pragma unroll
-            for (int t = 0; t < 4; t++) visit(cl[t] + LPR * k <= ch[t] ? __ldg(VS + ro[t] + cl[t] + LPR * k) : -1);
+                for (int t = 0; t < 4; t++) visit(cl[t] + LPR * k <= ch[t] ? __ldg(VS + ro[t] + cl[t] + LPR * k) : -1);
+            }
         }
     }
 }
@@ -540,8 +545,7 @@ bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st,
     const int L1 = P.L1 > 0 ? P.L1 : 0;
     if (dm.D > 254 || (2 * L1 + 1) * (2 * L1 + 1) > 65535) return false;
     if ((long long)dm.N * ((dm.D + 1) / 2) > dm.vol_stride) return false;   // histograms live in the idle cost volume
-    static int force_enum = -1;   // ADC_VOTE_ENUM=1: exercise the enumeration fallback (tests)
-    if (force_enum < 0) { const char* m = getenv("ADC_VOTE_ENUM"); force_enum = m ? atoi(m) : 0; }
+    const int force_enum = (P.dbg & 2) ? 1 : 0;   // ADC_DBG_VOTE_ENUM: exercise the enumeration fallback (tests)
     cudaMemsetAsync(w.vote_pslotT, 0xff, (size_t)w.S * dm.N * sizeof(int), st);
     dim3 tgrid((dm.W + 31) / 32, (dm.H + 31) / 32, w.S);
     k_vote_transpose<<<tgrid, 256, 0, st>>>(dm, w.arms, w.vote_atbT);
@@ -559,13 +563,12 @@ bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st,
     const size_t fixed = (size_t)VP_WARPS * cols_cap * 2;
     int slot_cap = (int)((220 * 1024 - fixed - 16) / 6) & ~15;
     if (slot_cap > VP_SMEM_SLOTS) slot_cap = VP_SMEM_SLOTS;
-    static int cap_override = -1;   // ADC_VOTE_SLOTCAP: shrink the shared-memory slot capacity (tests of the global-memory state)
-    if (cap_override < 0) { const char* m = getenv("ADC_VOTE_SLOTCAP"); cap_override = m ? atoi(m) : 0; }
-    if (cap_override > 0 && cap_override < slot_cap) slot_cap = cap_override & ~15;
+    if ((P.dbg & 4) && slot_cap > 256) slot_cap = 256;   // ADC_DBG_VOTE_GLOBAL_STATE: global-memory copy of the per-slot state (tests)
     const size_t smem = fixed + 2 * (size_t)slot_cap + ((size_t)slot_cap + 1) * 4;
-    static bool attr_done[64] = {};
-    if (adc_first_time_on_device(attr_done)) {
+    static AdcOnce attr_once;
+    if (adc_once_needed(attr_once)) {
         cudaFuncSetAttribute(k_vote_push, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);   // (+ static < 227 KB)
+        adc_once_done(attr_once);
     }
     k_vote_push<<<w.S, VP_THREADS, smem, st>>>(P, w.vote_alr, w.vote_atbT, w.vote_pslotT, w.pend, hist, dm.vol_stride,
                                               w.vote_off, w.vote_val, w.vote_dirtyb, w.vlist, w.counters, w.last_eval,

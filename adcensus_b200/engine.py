@@ -47,8 +47,11 @@ assert ctypes.sizeof(ADCensusOption) == 60
 
 class _Config(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int32), ("wave_pairs", ctypes.c_int32), ("lanes", ctypes.c_int32),
-                ("force_generic", ctypes.c_int32), ("use_graphs", ctypes.c_int32), ("async_refine", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 10)]
+                ("debug_flags", ctypes.c_int32), ("reserved", ctypes.c_int32 * 12)]
+
+
+# adc_config.debug_flags (test hooks)
+DBG_NO_RAY_TABLE, DBG_VOTE_ENUM, DBG_VOTE_GLOBAL_STATE, DBG_UNFUSED_AGG = 1, 2, 4, 8
 
 
 class AdcError(RuntimeError):
@@ -79,6 +82,7 @@ def load_library() -> ctypes.CDLL:
     L.adc_destroy.argtypes = [vp]
     L.adc_destroy.restype = None
     L.adc_match.argtypes = [vp, u8p, u8p, f32p]
+    L.adc_get_right_disparity.argtypes = [vp, f32p]
     L.adc_match_batch.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
     L.adc_match_batch_strided.argtypes = [vp, i32, u8p, u8p, f32p]
     L.adc_match_batch_device.argtypes = [vp, i32, u8p, u8p, f32p, vp]
@@ -123,12 +127,12 @@ class Engine:
     """Thin object wrapper over adc_create/.../adc_destroy."""
 
     def __init__(self, width: int, height: int, option: ADCensusOption | None = None, device: int = 0,
-                 wave_pairs: int = 0, lanes: int = 0, async_refine: bool = False):
+                 wave_pairs: int = 0, lanes: int = 0, debug_flags: int = 0):
         self._L = load_library()
         self.width, self.height = int(width), int(height)
         self.option = option or ADCensusOption()
         self.D = self.option.max_disparity - self.option.min_disparity
-        cfg = _Config(device=device, wave_pairs=wave_pairs, lanes=lanes, async_refine=1 if async_refine else 0)
+        cfg = _Config(device=device, wave_pairs=wave_pairs, lanes=lanes, debug_flags=debug_flags)
         h = ctypes.c_void_p()
         _check(self._L.adc_create(self.width, self.height, ctypes.byref(self.option), ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h
@@ -153,6 +157,12 @@ class Engine:
         right = _img(right, (self.height, self.width, 3))
         disp = np.empty((self.height, self.width), np.float32)
         _check(self._L.adc_match(self._h, left.ctypes.data, right.ctypes.data, disp.ctypes.data))
+        return disp
+
+    def right_disparity(self) -> np.ndarray:
+        """Right-view map of the most recent match() (the reference's private disp_right_)."""
+        disp = np.empty((self.height, self.width), np.float32)
+        _check(self._L.adc_get_right_disparity(self._h, disp.ctypes.data))
         return disp
 
     def match_batch(self, lefts, rights) -> np.ndarray:
@@ -196,7 +206,8 @@ class Engine:
         _check(self._L.adc_last_stage_ms(self._h, ctypes.byref(out)))
         return list(out)
 
-    PROFILE_KERNELS = {"cost_volume": 0, "arm_sum_h": 1, "arm_sum_v_div": 2, "scanline_x": 3, "scanline_y": 4, "wta": 5}
+    PROFILE_KERNELS = {"cost_volume": 0, "arm_sum_h": 1, "arm_sum_v_div": 2, "scanline_x": 3, "scanline_y": 4, "wta": 5,
+                       "arm_sum2_v": 6, "arm_sum2_h": 7, "arm_sum_h_div": 8}
 
     def profile_kernel(self, name: str, reps: int = 5):
         """(mean ms per launch over one wave, algorithmic bytes per launch) of one pipeline kernel."""

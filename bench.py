@@ -115,8 +115,8 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "maps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000 * wall / max(1, args.steps), 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": PAIRS_PER_STEP,
-                       "note": "each CPU step is a bounded sample of the workload (one Cone pair per host core)"},
+            "config": dict(_config_dict(WORKLOAD, PAIRS_PER_STEP, 450, 375, 64),
+                           note="each CPU step is a bounded sample of the workload (one Cone pair per host core)"),
             "cpu_baseline": res,
             "e2e": {"value": value, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -161,6 +161,60 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _config_dict(wl_name, n, w, h, D, eng=None, world=1, pipelined=True, sharded=False):
+    """The `config` object of the JSON line -- built the same way by both arms so that the driver can compare them."""
+    c = {"workload": wl_name, "pairs_per_step_per_gpu": n, "width": w, "height": h, "disparities": D}
+    if eng is not None:
+        c.update({"wave_pairs": eng.wave_pairs, "lanes": eng.lanes, "steps_pipelined": pipelined,
+                  "l2_policy": "no flush needed: each step streams the whole batch of images and several GB of cost volumes per wave, far beyond the 126 MB L2",
+                  "parallelism": (f"dp{world}, one batch owned by rank 0: NCCL scatter of the inputs, per-rank Match, NCCL gather of the maps"
+                                  if sharded else f"dp{world} (independent pairs, no data-path collective)")})
+    return c
+
+
+def _golden_final_sha(workload):
+    """sha256 of the final map(s) the UNMODIFIED reference produced for this workload's inputs (tests/golden)."""
+    import adc_testlib as T
+    if workload == "cone":
+        z = np.load(T.GOLDEN_DIR / "golden_cone_full.npz")
+        return {0: json.loads(str(z["hashes"]))["MEDIAN/DISP_L"]}
+    big = json.loads((T.GOLDEN_DIR / "golden_big.json").read_text())
+    if workload == "kitti":
+        return {0: big["kitti_s1"]["hashes"]["MEDIAN/DISP_L"], 1: big["kitti_s2"]["hashes"]["MEDIAN/DISP_L"]}
+    return {0: big["p1080_s1"]["hashes"]["MEDIAN/DISP_L"]}
+
+
+def reference_single_instance(left, right, dmax):
+    """ONE instance of the reference on one otherwise idle core -- Match wall time (median of
+    5) and the split over the stages its own timers print (ADCensusStereo.cpp:88-129), taken with the staged runner."""
+    import adc_testlib as T
+    T.build_oracle()
+    kind = "reference" if T.have_ref() else "port"
+    h, w, _ = left.shape
+    mk = (lambda: T.Reference(w, h, T.default_option(max_disparity=dmax))) if kind == "reference" else \
+         (lambda: T.Oracle(w, h, T.default_option(max_disparity=dmax)))
+    eng = mk()
+    tot = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        eng.time_match(left, right, 1)
+        tot.append(time.perf_counter() - t0)
+    groups = {"cost": ["COST"], "aggregation": ["ARMS", "AGG1", "AGG2", "AGG3", "AGG4"], "scanline": ["SO1", "SO2", "SO3", "SO4"],
+              "wta": ["WTA"], "refine": ["OUTLIER", "VOTE", "INTERP", "DISC", "MEDIAN"]}
+    split = {k: 0.0 for k in groups}
+    eng.begin(left, right)
+    for st in T.STAGES:
+        t0 = time.perf_counter()
+        eng.step()
+        dt = time.perf_counter() - t0
+        for k, v in groups.items():
+            if st in v:
+                split[k] += dt
+    eng.close()
+    return {"kind": kind, "cores": 1, "s_per_map_median_of_5": round(statistics.median(tot), 4),
+            "stage_s": {k: round(v, 4) for k, v in split.items()}}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -179,6 +233,7 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
 
     # workloads: BASELINE.json configs[1] (the contract's metric) by default; configs[2] / configs[3] on request
+    seeds = 1
     if args.workload == "cone":
         left, right = T.load_cone()
         dmax_w, n, wl_name = 64, PAIRS_PER_STEP, WORKLOAD
@@ -191,6 +246,11 @@ def run_gpu_arm(args):
         lefts = np.stack([pairs[i % seeds][0] for i in range(n)])
         rights = np.stack([pairs[i % seeds][1] for i in range(n)])
         left, right = pairs[0]
+    if args.pairs > 0:
+        n = args.pairs
+        if lefts is not None:
+            lefts = np.stack([pairs[i % seeds][0] for i in range(n)])
+            rights = np.stack([pairs[i % seeds][1] for i in range(n)])
     h, w, _ = left.shape
     # job descriptor from rank 0 (the only data-path collective besides the final reductions)
     desc = torch.tensor([w, h, 0, dmax_w, n], dtype=torch.int32, device=dev)
@@ -202,8 +262,10 @@ def run_gpu_arm(args):
     eng = A.Engine(w, h, opt, device=local, wave_pairs=args.wave_pairs, lanes=args.lanes)
     eng.set_pipelined(not args.no_pipeline)
     N = w * h
-    h_left = torch.from_numpy(np.repeat(left[None], n, 0) if lefts is None else lefts).pin_memory()
-    h_right = torch.from_numpy(np.repeat(right[None], n, 0) if rights is None else rights).pin_memory()
+    np_left = np.repeat(left[None], n, 0) if lefts is None else lefts
+    np_right = np.repeat(right[None], n, 0) if rights is None else rights
+    h_left = torch.from_numpy(np_left).pin_memory()
+    h_right = torch.from_numpy(np_right).pin_memory()
     h_disp = torch.empty((n, h, w), dtype=torch.float32).pin_memory()
     d_left, d_right = h_left.to(dev), h_right.to(dev)
     d_disp = torch.empty((n, h, w), dtype=torch.float32, device=dev)
@@ -215,14 +277,15 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, join=True):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = eng.launch_count
         e0.record(st)
         for _ in range(steps):
             fn()
-        eng.join(st.cuda_stream)        # pipelined engine: the K steps flow into each other, the join is inside the timed region
+        if join:
+            eng.join(st.cuda_stream)    # pipelined engine: the K steps flow into each other, the join is inside the timed region
         e1.record(st)
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -232,6 +295,9 @@ def run_gpu_arm(args):
             dist.all_reduce(launches, op=dist.ReduceOp.SUM)
         barrier()
         return float(ms.item()), int(launches.item())
+
+    if args.sharded:
+        return run_sharded_arm(args, eng, dev, rank, world, n, w, h, dmax - dmin, wl_name, np_left, np_right, timed, barrier)
 
     dev_step = lambda: eng.match_batch_device(n, d_left.data_ptr(), d_right.data_ptr(), d_disp.data_ptr(), st.cuda_stream)
     e2e_step = lambda: eng.match_batch_pinned_async(n, h_left.data_ptr(), h_right.data_ptr(), h_disp.data_ptr(), st.cuda_stream)
@@ -249,51 +315,102 @@ def run_gpu_arm(args):
     eng.join(st.cuda_stream)
     ms_e2e, _ = timed(e2e_step, args.steps)
 
-    # correctness guard inside the bench: every map of the batch must equal the single-pair result
-    ref_map = eng.match(left, right)
-    torch.cuda.synchronize()
-    if lefts is None:
-        ok = bool((h_disp.numpy().view(np.uint32) == ref_map.view(np.uint32)[None]).all())
-        okd = bool((d_disp.cpu().numpy().view(np.uint32) == ref_map.view(np.uint32)[None]).all())
-    else:   # cycled distinct pairs: every copy of pair 0 must equal its single-pair map, and both paths must agree
-        idx = np.arange(0, n, seeds)
-        ok = bool((h_disp.numpy()[idx].view(np.uint32) == ref_map.view(np.uint32)[None]).all())
-        okd = bool(np.array_equal(d_disp.cpu().numpy().view(np.uint32), h_disp.numpy().view(np.uint32)))
+    # correctness guard inside the bench: the maps of the timed runs against the sha256 of the map the UNMODIFIED
+    # reference produced for the same input (tests/golden, generated by tools/make_golden*.py from oracle/_ref);
+    # every other copy of a pair must equal the checked one, and the device and host paths must agree
+    golden = _golden_final_sha(args.workload)
+    hd, dd = h_disp.numpy(), d_disp.cpu().numpy()
+    ok = all(T.sha(hd[i]) == sha for i, sha in golden.items())
+    for s0 in range(min(seeds, n)):
+        ok = ok and bool((hd[s0::seeds].view(np.uint32) == hd[s0].view(np.uint32)[None]).all())
+    okd = bool(np.array_equal(dd.view(np.uint32), hd.view(np.uint32)))
     flag = torch.tensor([int(ok and okd)], dtype=torch.int32, device=dev)
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 
     line = None
     if rank == 0:
+        # ---- the reference's contract literally: pageable host buffers through the synchronous batch call
+        eng.set_pipelined(False)
+        pg_disp = np.empty((n, h, w), np.float32)
+        eng._L.adc_match_batch_strided(eng._h, n, np_left.ctypes.data, np_right.ctypes.data, pg_disp.ctypes.data)   # warm-up
+        t0 = time.perf_counter()
+        reps_pg = max(1, min(args.steps, 3))
+        for _ in range(reps_pg):
+            rc = eng._L.adc_match_batch_strided(eng._h, n, np_left.ctypes.data, np_right.ctypes.data, pg_disp.ctypes.data)
+        t_pg = (time.perf_counter() - t0) / reps_pg
+        pageable = {"value": round(n / t_pg, 2), "unit": "maps/s", "ms_per_step": round(1000 * t_pg, 3),
+                    "call": "adc_match_batch_strided on pageable numpy arrays (host wall clock; staging through the engine's pinned ring)",
+                    "bit_identical": bool(rc == 0 and np.array_equal(pg_disp.view(np.uint32), hd.view(np.uint32)))}
+        # ---- one pair at a time: ADCensusStereo::Match as the reference's caller uses it (main.cpp:118)
+        lat, stages = [], []
+        for _ in range(25):
+            t0 = time.perf_counter()
+            eng.match(left, right)
+            lat.append(1000 * (time.perf_counter() - t0))
+            stages.append(eng.last_stage_ms())
+        lat, stages = lat[5:], stages[5:]
+        single = {"match_ms_median_of_20": round(statistics.median(lat), 3),
+                  "stage_ms_median": dict(zip(("cost", "aggregation", "scanline", "wta", "refine", "copy_out"),
+                                              [round(statistics.median(c), 3) for c in zip(*stages)])),
+                  "note": "adc_match: pageable host pointers in, host map out, synchronous; stage times from CUDA events"}
+        eng.set_pipelined(not args.no_pipeline)
+
         peaks = {}
         pk = ROOT / "MEASURED_PEAKS.json"
         if pk.exists():
             peaks = json.loads(pk.read_text())
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        V, Nf = 4.0 * N * (dmax - dmin), float(N)
         kern = {}
-        for name in ("cost_volume", "arm_sum_h", "arm_sum_v_div", "scanline_x", "scanline_y", "wta"):
-            kms, kbytes = eng.profile_kernel(name, reps=5)
+        names = ["cost_volume", "arm_sum_h", "arm_sum2_v", "arm_sum2_h", "arm_sum_h_div", "arm_sum_v_div", "scanline_x", "scanline_y", "wta"]
+        for name in names:
+            try:
+                kms, kbytes = eng.profile_kernel(name, reps=5)
+            except A.AdcError:
+                continue
             kern[name] = {"ms_per_launch": round(kms, 4), "algorithmic_bytes": kbytes,
                           "achieved_gbs": round(kbytes / (kms * 1e-3) / 1e9, 1),
                           "frac": round(kbytes / (kms * 1e-3) / 1e9 / hbm_peak, 4), "pairs_per_launch": eng.wave_pairs}
-        # dominant kernel of a step = the one with the largest share of device time:
-        # 8 arm-sum launches and 4 scanline launches per wave
-        share = {"arm_sum": 4 * (kern["arm_sum_h"]["ms_per_launch"] + kern["arm_sum_v_div"]["ms_per_launch"]),
-                 "scanline": 2 * (kern["scanline_x"]["ms_per_launch"] + kern["scanline_y"]["ms_per_launch"])}
-        dom = "scanline_x" if share["scanline"] >= share["arm_sum"] else "arm_sum_v_div"
+        # Aggregation STAGE on SURVEY 8(d)'s bytes: (2V + 6N) per ITERATION (the first-pass result is an on-chip intermediate
+        # in that model), four iterations, against the time of ALL its launches of a wave (kernels timed alone, CUDA events).
+        fused = "arm_sum2_v" in kern and "arm_sum2_h" in kern
+        if fused:
+            agg_ms = (kern["arm_sum_h"]["ms_per_launch"] + 2 * kern["arm_sum2_v"]["ms_per_launch"] +
+                      kern["arm_sum2_h"]["ms_per_launch"] + kern["arm_sum_h_div"]["ms_per_launch"])
+            agg_launches, agg_transfers = 5, 10
+        else:
+            agg_ms = 4 * (kern["arm_sum_h"]["ms_per_launch"] + kern["arm_sum_v_div"]["ms_per_launch"])
+            agg_launches, agg_transfers = 8, 16
+        agg_bytes = 4 * (2 * V + 6 * Nf) * eng.wave_pairs
+        aggregation = {"model": "SURVEY 8(d): (2V + 6N) per iteration x 4 iterations per pair", "launches_per_wave": agg_launches,
+                       "volume_transfers_per_pair": agg_transfers, "ms_per_wave": round(agg_ms, 4),
+                       "achieved_gbs": round(agg_bytes / (agg_ms * 1e-3) / 1e9, 1),
+                       "frac": round(agg_bytes / (agg_ms * 1e-3) / 1e9 / hbm_peak, 4)}
+        so_ms = 2 * (kern["scanline_x"]["ms_per_launch"] + kern["scanline_y"]["ms_per_launch"])
+        # dominant kernel of a step = the launch kind with the largest share of device time
+        if fused:
+            share = {"arm_sum2_v": 2 * kern["arm_sum2_v"]["ms_per_launch"], "arm_sum2_h": kern["arm_sum2_h"]["ms_per_launch"],
+                     "scanline_x": so_ms / 2, "scanline_y": so_ms / 2}
+        else:
+            share = {"arm_sum_v_div": agg_ms / 2, "arm_sum_h": agg_ms / 2, "scanline_x": so_ms / 2, "scanline_y": so_ms / 2}
+        dom = max(share, key=share.get)
         # measured DRAM bytes of that kernel (ncu --set full capture summarised in profiles/; per pair there, per launch here)
-        traffic = None
+        traffic, tsrc = None, None
         tf = ROOT / "profiles" / "traffic.json"
         if tf.exists():
-            per_pair = json.loads(tf.read_text()).get(dom, {}).get("dram_bytes_per_pair")
+            tj = json.loads(tf.read_text())
+            per_pair = tj.get(dom, {}).get("dram_bytes_per_pair")
+            tsrc = tj.get("_source")
             if per_pair:
                 traffic = round(per_pair * eng.wave_pairs)
         roof = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": kern[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                "note": "algorithmic bytes per launch = (2V + 6N) per pair x pairs per launch, V = 4*H*W*D (SURVEY 8d); "
-                        "traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture "
-                        "(profiles/r1_ncu_full_v32_summary.csv); kernel timed alone with CUDA events on the engine's stream"}
+                "note": "algorithmic bytes per launch = (2V + 6N) per pair x pairs per launch, V = 4*H*W*D: the kernel reads one volume and "
+                        "writes one (a fused double pass keeps its intermediate in shared memory; it does one iteration's worth of work per "
+                        "launch, SURVEY 8d); traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture "
+                        f"({tsrc}); kernel timed alone with CUDA events on the engine's stream; 'aggregation' below is the whole stage on the 8(d) model"}
         total_maps = world * n * args.steps
         value = total_maps / (ms_dev * 1e-3)
         e2e_v = total_maps / (ms_e2e * 1e-3)
@@ -303,19 +420,81 @@ def run_gpu_arm(args):
         line = {"metric": metric, "value": round(value, 2), "unit": "maps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": wl_name, "pairs_per_step_per_gpu": n, "width": w, "height": h, "disparities": dmax - dmin,
-                           "wave_pairs": eng.wave_pairs, "lanes": eng.lanes,
-                           "steps_pipelined": not args.no_pipeline,
-                           "l2_policy": "no flush needed: each step streams the whole batch of images and several GB of cost volumes per wave, far beyond the 126 MB L2",
-                           "parallelism": f"dp{world} (independent pairs, no data-path collective)"},
+                "config": _config_dict(wl_name, n, w, h, dmax - dmin, eng, world, not args.no_pipeline),
                 "e2e": {"value": round(e2e_v, 2), "unit": "maps/s", "h2d_bytes_per_step": n * 2 * N * 3,
-                        "d2h_bytes_per_step": n * N * 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
+                        "d2h_bytes_per_step": n * N * 4, "ms_per_step": round(ms_e2e / args.steps, 3),
+                        "call": "adc_match_batch_pinned_async on pinned host buffers + adc_join"},
+                "e2e_pageable": pageable, "single_pair": single,
                 "gpu_launches": launches, "clocks": clocks, "outputs_bit_identical": bool(flag.item()),
+                "outputs_checked_against": "sha256 of the unmodified reference's map (tests/golden), every copy, device and host path",
                 "pipeline_hbm": {"algorithmic_bytes_per_map": b_map, "achieved_gbs": round(value * b_map / 1e9 / world, 1),
                                  "frac": round(value * b_map / 1e9 / world / hbm_peak, 4)},
-                "roofline": roof, "kernels": kern}
+                "roofline": roof, "aggregation": aggregation, "kernels": kern}
         if cpu:
+            cpu["single_instance"] = reference_single_instance(left, right, dmax)
             line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_sharded_arm(args, eng, dev, rank, world, n, w, h, D, wl_name, np_left, np_right, timed, barrier):
+    """BASELINE.json configs[4]: ONE batch of n x world pairs owned by rank 0 (resident in its HBM), scattered over the
+    ranks with NCCL, matched by every rank's engine, the maps gathered back on rank 0 with NCCL.  A step =
+    scatter + Match + gather of the whole batch; value = pairs / max-over-ranks time."""
+    import torch
+    import torch.distributed as dist
+    import adc_testlib as T
+    from adcensus_b200.parallel import run_sharded_device
+    N, total = w * h, n * world
+    seeds = 16 if args.workload == "kitti" else (8 if args.workload == "1080p" else 1)
+    st = torch.cuda.current_stream()
+    d_l = d_r = d_out = None
+    if rank == 0:
+        reps = (total + n - 1) // n
+        d_l = torch.from_numpy(np_left).to(dev).repeat((reps, 1, 1, 1))[:total].contiguous()   # n is a multiple of the seed cycle
+        d_r = torch.from_numpy(np_right).to(dev).repeat((reps, 1, 1, 1))[:total].contiguous()
+        d_out = torch.empty((total, h, w), dtype=torch.float32, device=dev)
+    phases = {}
+    step = lambda: run_sharded_device(eng, d_l, d_r, d_out, total, h, w, dev, phases)
+    for _ in range(max(1, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches = timed(step, args.steps, join=False)
+    clocks = sampler.stop() if sampler else None
+    if "resolve" in phases:
+        phases["resolve"]()
+    ok = True
+    if rank == 0:
+        golden = _golden_final_sha(args.workload)
+        out = d_out.cpu().numpy()
+        ok = all(T.sha(out[i]) == sha for i, sha in golden.items())
+        for s0 in range(min(seeds, total)):
+            ok = ok and bool((out[s0::seeds].view(np.uint32) == out[s0].view(np.uint32)[None]).all())
+    flag = torch.tensor([int(ok)], dtype=torch.int32, device=dev)
+    ph = torch.tensor([phases.get("scatter_ms", 0.0), phases.get("compute_ms", 0.0), phases.get("gather_ms", 0.0)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        value = total * args.steps / (ms * 1e-3)
+        metric = METRIC if args.workload == "cone" else f"disparity-maps/sec ({w}x{h}x{D})"
+        line = {"metric": metric, "value": round(value, 2), "unit": "maps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(1, args.warmup), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(_config_dict(wl_name, n, w, h, D, eng, world, False, sharded=True), batch_owned_by_rank0=total),
+                "sharded": {"total_pairs": total, "scatter_bytes": (total - n) * 2 * N * 3, "gather_bytes": (total - n) * N * 4,
+                            "last_step_ms_max_over_ranks": {"scatter": round(float(ph[0]), 3), "compute": round(float(ph[1]), 3),
+                                                            "gather": round(float(ph[2]), 3)},
+                            "note": "inputs and results resident in rank 0's HBM; NCCL point-to-point scatter / gather; phases timed with CUDA events "
+                                    "on each rank's stream (the phases of different ranks overlap, so they do not add up to the step)"},
+                "gpu_launches": launches, "clocks": clocks, "outputs_bit_identical": bool(flag.item()),
+                "outputs_checked_against": "sha256 of the unmodified reference's maps (tests/golden) + every copy of a pair equal, gathered order"}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
@@ -334,6 +513,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="join the stream after every step (adc_set_pipelined off): each step then drains the engine")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per step per GPU (default: the BASELINE batch of the workload)")
+    ap.add_argument("--sharded", action="store_true",
+                    help="BASELINE configs[4] form: one batch of pairs x gpus owned by rank 0, NCCL scatter -> Match -> NCCL gather")
     ap.add_argument("--workload", default="cone", choices=["cone", "kitti", "1080p"],
                     help="cone = BASELINE configs[1] (the contract metric); kitti / 1080p = configs[2] / configs[3] (extra lines)")
     args = ap.parse_args()

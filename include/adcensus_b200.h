@@ -59,19 +59,31 @@ typedef struct adc_config {
     int32_t device;          /* CUDA device ordinal */
     int32_t wave_pairs;      /* stereo pairs processed by one batched kernel launch (default: auto) */
     int32_t lanes;           /* concurrent waves in flight, one stream each (default: auto) */
-    int32_t force_generic;   /* 1: always use the unfused per-pass kernels (the path the debug taps see) */
-    int32_t use_graphs;      /* 1: replay each wave as a CUDA graph */
-    int32_t async_refine;    /* 1: a lane runs the refinement stage of wave k on a second stream, on its own buffer set,
-                                while its first stream already streams the volumes of wave k+1 (experimental, off) */
-    int32_t reserved[10];
+    int32_t debug_flags;     /* test hooks, 0 in production: force the alternate code paths that otherwise only unusual
+                                parameters reach, so that the parity tests can run every shipped kernel (ADC_DBG_*) */
+    int32_t reserved[12];    /* must be zero */
 } adc_config;
+
+enum {
+    ADC_DBG_NO_RAY_TABLE = 1,     /* interpolation evaluates lround(y + m*sin) in double per step instead of the verified integer table */
+    ADC_DBG_VOTE_ENUM = 2,        /* region voting finds the affected histograms by enumeration instead of adjacency lists */
+    ADC_DBG_VOTE_GLOBAL_STATE = 4,/* region voting keeps its per-slot state in global instead of shared memory */
+    ADC_DBG_UNFUSED_AGG = 8       /* aggregation as eight single passes instead of five (three of them fused double passes) */
+};
 
 /* stands in for: ADCensusOption::ADCensusOption() defaults (adcensus_types.h:67-74) */
 void adc_default_option(adc_option* opt);
 
+/* Sizes the kernels implement; the reference has no such limits (it only rejects non-positive sizes).  A configuration
+ * outside them fails at adc_create / Initialize with ADC_ERR_UNSUPPORTED -- never later, in adc_match. */
+#define ADC_MAX_DISPARITY_RANGE 256   /* max_disparity - min_disparity */
+#define ADC_MAX_HEIGHT 4096
+#define ADC_MAX_WIDTH 10000           /* also bounds width + disparity range */
+
 /* stands in for: ADCensusStereo::Initialize(width, height, option) (ADCensusStereo.h:25,
  * ADCensusStereo.cpp:21-67).  cfg may be NULL.  Fails (ADC_ERR_ARG) exactly where Initialize
- * returns false: width<=0, height<=0, max_disparity-min_disparity<=0. */
+ * returns false: width<=0, height<=0, max_disparity-min_disparity<=0; fails with ADC_ERR_UNSUPPORTED beyond the
+ * limits above. */
 int adc_create(int32_t width, int32_t height, const adc_option* opt, const adc_config* cfg, adc_engine** out);
 
 /* stands in for: ADCensusStereo::~ADCensusStereo / Release (ADCensusStereo.cpp:15-19,312-316) */
@@ -81,6 +93,12 @@ void adc_destroy(adc_engine* e);
  * ADCensusStereo.cpp:69-132).  Packed BGR u8 [H][W][3] host images (main.cpp:61-76), caller-
  * allocated float32 [H][W] host output, +inf = invalid.  Synchronous. */
 int adc_match(adc_engine* e, const uint8_t* img_left, const uint8_t* img_right, float* disp_left);
+
+/* The right-view disparity map of the most recent adc_match call: what the reference computes into its private
+ * disp_right_ (ADCensusStereo::ComputeDisparityRight, ADCensusStereo.cpp:245-310) for the left-right check and never
+ * hands out -- float32 [H][W], sub-pixel, not refined (a minimum at either end of the range is the integer disparity).
+ * Host pointer.  SURVEY.md 8(f) rank 4. */
+int adc_get_right_disparity(adc_engine* e, float* disp_right);
 
 /* Batched Match over n independent pairs (the data-parallel form of the call above; the
  * reference would loop Match).  Pointers are host pointers; pinned buffers are copied
@@ -129,7 +147,9 @@ int adc_get_config(const adc_engine* e, adc_config* out);
 
 /* Times one kernel of the pipeline in isolation on the engine's own stream (CUDA events), over one
  * wave of wave_pairs pairs: kernel_id 0 = cost volume, 1 = horizontal arm sum, 2 = vertical arm sum
- * with division, 3 = scanline pass along x, 4 = scanline pass along y, 5 = WTA left+right.
+ * with division, 3 = scanline pass along x, 4 = scanline pass along y, 5 = WTA left+right, 6 / 7 = the fused
+ * vertical / horizontal double pass of the aggregation (divide + sum, intermediate in shared memory), 8 = horizontal
+ * arm sum with division.
  * algorithmic_bytes (optional) receives the bytes one launch must move. */
 int adc_profile_kernel(adc_engine* e, int32_t kernel_id, int32_t reps, float* avg_ms, double* algorithmic_bytes);
 
@@ -149,8 +169,9 @@ const char* adc_last_error(void);
 const char* adc_version(void);
 
 /* ---- debug taps (parity tests) -------------------------------------------------------------
- * adc_debug_run executes the pipeline on ONE pair up to and including `last_stage` with the
- * unfused kernels and leaves every buffer live; adc_debug_get copies a buffer out in the
+ * adc_debug_run executes the production pipeline on ONE pair up to and including `last_stage` and leaves every
+ * buffer live (a run that stops between two aggregation iterations, AGG1..AGG3, takes the eight single aggregation
+ * passes instead of the fused same-axis passes, whose intermediate never reaches memory); adc_debug_get copies a buffer out in the
  * reference's layout ([H][W][D] with d fastest for the volumes).  Stage and tap ids follow the
  * reference's structure: stages are the steps of Match / Aggregate / Optimize / Refine, taps are
  * the private members a parity test wants to see (cost_computor.h:80-91, cross_aggregator.h:88-102,

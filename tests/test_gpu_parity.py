@@ -54,6 +54,14 @@ CASES = [
     (80, 60, 32, {"min_disparity": 2, "max_disparity": 34}, 31),     # dmin > 0
     (80, 60, 32, {"min_disparity": -4, "max_disparity": 28}, 32),    # negative dmin
     (200, 40, 200, {}, 13),         # a whole warp per line
+    (300, 24, 256, {}, 14),         # the largest range: 8 WTA chunks, voting with int state (D > 254: k_region_voting_global)
+    (64, 40, 255, {}, 15),          # D = 255 (padded to 256), same voting path
+    (90, 200, 16, {"cross_L1": 70, "cross_L2": 30, "cross_t1": 300, "cross_t2": 300}, 16),   # arms never stop on colour: cross
+    #                                 regions of up to 141 rows (the voting scan works in 96-row chunks), 141-tap windows
+    (60, 300, 16, {"cross_L1": 130, "cross_L2": 17, "cross_t1": 300, "cross_t2": 300}, 17),  # L1 > 127: byte-state pull voting
+    #                                 (k_region_voting_bytes), fused aggregation with a larger shared-memory budget
+    (700, 20, 12, {}, 18),          # a long row: the horizontal double pass of the aggregation cut into segments
+    (33, 21, 5, {}, 19),            # D < 8: a single padded quad pair per pixel
 ]
 
 
@@ -168,49 +176,10 @@ def test_cone_final_equals_reference_golden(cone):
     eng.close()
 
 
-@pytest.mark.parametrize("shape", [(1242, 375, 128), (1920, 1080, 192)], ids=["kitti_shape", "1080p"])
-def test_full_size_properties(shape):
-    """BASELINE configs 3/4 shapes.  Size-independent properties (the oracle needs 16 s / 115 s per
-    pair here): (1) the synthetic pair has a known band disparity -> the map must recover it away
-    from band edges / borders; (2) batch == single, bit for bit; (3) determinism."""
-    w, h, D = shape
-    opt = T.default_option(max_disparity=D)
-    left, right = T.synthetic_pair(w, h, D, 1)
-    eng = _engine(w, h, opt)
-    a = eng.match(left, right)
-    b = eng.match(left, right)
-    assert a.view(np.uint32).tobytes() == b.view(np.uint32).tobytes()
-    batch = eng.match_batch(np.stack([left, left, left]), np.stack([right, right, right]))
-    assert (batch.view(np.uint32) == a.view(np.uint32)[None]).all()
-    # ground truth: right(x) = left(x + d_band)  ->  disparity d_band on rows of the band
-    lo, span = D // 8, max(1, (3 * D) // 4 - D // 8)
-    bands = T._splitmix64(np.uint64(1) * np.uint64(1000003) + (np.arange(h) // 25).astype(np.uint64))
-    truth = (lo + (bands % np.uint64(span)).astype(np.int64)).astype(np.float32)[:, None]
-    inner = np.zeros((h, w), bool)
-    for y in range(h):
-        if 6 <= y % 25 <= 18:
-            inner[y, D:w - 8] = True
-    err = np.abs(a - truth)
-    good = (err[inner] <= 1.0).mean()
-    assert good > 0.9, f"only {good:.3f} of interior pixels within 1 px of the synthetic ground truth"
-    eng.close()
-
-
-def test_kitti_shape_vs_oracle():
-    """One full-size 1242x375x128 pair against the CPU oracle (about 16 s of CPU)."""
-    w, h, D = 1242, 375, 128
-    opt = T.default_option(max_disparity=D)
-    left, right = T.synthetic_pair(w, h, D, 3)
-    eng = _engine(w, h, opt)
-    got = eng.match(left, right)
-    want = T.Oracle(w, h, opt).match(left, right)
-    _same("kitti-shape final map", got, want)
-    eng.close()
-
-
-def test_cpp_dropin_program_on_gpu(tmp_path):
-    """The reference-style C++ caller (tests/cpp/dropin_main.cpp) really runs Match on the device."""
-    import os
+def test_cpp_dropin_program_on_gpu(tmp_path, cone):
+    """The reference-style C++ caller (tests/cpp/dropin_main.cpp, written against ADCensusStereo.h as main.cpp uses it)
+    runs Match on the Cone pair on the device; the map it writes must hash to the unmodified reference's."""
+    import json
     import subprocess
     import adcensus_b200 as A
     exe = tmp_path / "dropin"
@@ -218,53 +187,50 @@ def test_cpp_dropin_program_on_gpu(tmp_path):
                         f"-L{A.lib_path().parent}", "-ladcensus_b200", f"-Wl,-rpath,{A.lib_path().parent}", "-o", str(exe)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
-    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    left, right = cone
+    h, w, _ = left.shape
+    left.tofile(tmp_path / "left.bgr"); right.tofile(tmp_path / "right.bgr")
+    run = subprocess.run([str(exe), str(tmp_path / "left.bgr"), str(tmp_path / "right.bgr"), str(w), str(h), "0", "64",
+                          str(tmp_path / "disp.f32")], capture_output=True, text=True)
     assert run.returncode == 0 and "DROPIN_OK" in run.stdout, (run.returncode, run.stdout[-500:], run.stderr[-500:])
     assert "cost aggregating! timing" in run.stdout     # the reference's six timing lines are kept
+    got = np.fromfile(tmp_path / "disp.f32", np.float32).reshape(h, w)
+    hashes = json.loads(str(np.load(T.GOLDEN_DIR / "golden_cone_full.npz")["hashes"]))
+    assert T.sha(got) == hashes["MEDIAN/DISP_L"], "C++ drop-in class produced a different Cone map than the reference"
 
 
-@pytest.mark.parametrize("env", [{"ADC_VOTE_ENUM": "1"}, {"ADC_VOTE_SLOTCAP": "256"}], ids=["enumeration", "global-state"])
-def test_voting_fallback_paths(tmp_path, env):
-    """(enumeration) The voting kernel has two ways to find the histograms a filled pixel belongs to: precomputed adjacency lists
-    (default) and on-the-fly enumeration of the inverse cross region (when the lists would not fit).  The switch is
-    read once per process, so the fallback runs in a child: Cone and two synthetic cases through the VOTE stage and
-    the final map, against the oracle.
-    (global-state) Per-slot state lives in shared memory when the lists fit, else in global memory; a tiny capacity forces
-    the latter."""
-    import os, subprocess, sys, textwrap
-    script = tmp_path / "enum_case.py"
-    script.write_text(textwrap.dedent("""
-        import sys
-        sys.path.insert(0, %r); sys.path.insert(0, %r)
-        import numpy as np
-        import adc_testlib as T
-        import adcensus_b200 as A
-        cases = [T.load_cone() + (64,)]
-        for (w, h, D, seed) in ((120, 90, 48, 3), (97, 61, 24, 5)):
-            l, r = T.synthetic_pair(w, h, D, seed)
-            cases.append((l, r, D))
-        for left, right, D in cases:
-            h, w, _ = left.shape
-            opt = T.default_option(max_disparity=D)
-            orc = T.Oracle(w, h, opt)
-            eng = A.Engine(w, h, A.ADCensusOption(max_disparity=D))
-            orc.begin(left, right); orc.run_to("VOTE")
-            eng.debug_run(left, right, "VOTE")
-            c = eng.counters()   # [13] = 1 when the adjacency lists were used (they need room in the idle cost volume,
-            #                      which small images with long lists do not have -- Cone does)
-            if %r: assert c[13] == 0, f"adjacency lists used although ADC_VOTE_ENUM=1: counters {c}"
-            elif (w, h) == (450, 375): assert c[13] == 1, f"Cone fell back to enumeration: counters {c}"
-            for tap in ("DISP_L", "MISMATCHES", "OCCLUSIONS"):
-                g, o = eng.tap(tap), orc.tap(tap)
-                assert g.shape == o.shape and g.tobytes() == o.tobytes(), tap
-            want = orc.match(left, right)
-            assert eng.match(left, right).tobytes() == want.tobytes()
-            eng.close()
-        print("ok")
-    """ % (str(T.REPO), str(T.REPO / "tests"), "ADC_VOTE_ENUM" in env)))
-    env = dict(os.environ, **env)
-    r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+@pytest.mark.parametrize("flag", ["DBG_VOTE_ENUM", "DBG_VOTE_GLOBAL_STATE", "DBG_NO_RAY_TABLE", "DBG_UNFUSED_AGG"])
+def test_alternate_code_paths(flag, cone):
+    """Kernels that only unusual parameters reach, forced through adc_config.debug_flags, against the oracle:
+    DBG_VOTE_ENUM          the voting kernel finds the histograms a filled pixel belongs to by enumerating the inverse cross
+                           region instead of walking precomputed adjacency lists (taken when the lists do not fit);
+    DBG_VOTE_GLOBAL_STATE  its per-slot state in global instead of shared memory (more than 32768 pending pixels);
+    DBG_NO_RAY_TABLE       interpolation rays evaluated in double per step (image sizes for which the integer ray table is
+                           not exact);
+    DBG_UNFUSED_AGG        the eight single aggregation passes through the whole pipeline (arms too long for the fused plan)."""
+    import adcensus_b200 as A
+    fl = getattr(A.engine, flag)
+    cases = [cone + (64,)]
+    for (w, h, D, seed) in ((120, 90, 48, 3), (97, 61, 24, 5)):
+        l, r = T.synthetic_pair(w, h, D, seed)
+        cases.append((l, r, D))
+    for left, right, D in cases:
+        h, w, _ = left.shape
+        opt = T.default_option(max_disparity=D)
+        orc = T.Oracle(w, h, opt)
+        eng = _engine(w, h, opt, debug_flags=fl)
+        orc.begin(left, right); orc.run_to("VOTE")
+        eng.debug_run(left, right, "VOTE")
+        c = eng.counters()   # [13] = 1 when the adjacency lists were used (they need room in the idle cost volume,
+        #                      which small images with long lists do not have -- Cone does)
+        if flag == "DBG_VOTE_ENUM":
+            assert c[13] == 0, f"adjacency lists used although enumeration was forced: counters {c}"
+        elif (w, h) == (450, 375):
+            assert c[13] == 1, f"Cone fell back to enumeration: counters {c}"
+        for tap in ("DISP_L", "MISMATCHES", "OCCLUSIONS"):
+            _same(f"{flag} VOTE/{tap}", eng.tap(tap), orc.tap(tap))
+        _same(f"{flag} final", eng.match(left, right), orc.match(left, right))
+        eng.close()
 
 
 def test_pipelined_batches(cone):
@@ -295,27 +261,164 @@ def test_pipelined_batches(cone):
     eng.close()
 
 
-def test_async_refine_lanes(cone):
-    """adc_config.async_refine (experimental): a lane's refinement stage on a second stream with its own buffer set while
-    the first stream streams the next wave's volumes.  Same bits as the plain schedule, over several waves per lane."""
-    import torch
+def test_limits_fail_at_create_not_at_match():
+    """The reference has no size limits (ADCensusStereo.cpp:31-41 only rejects non-positive sizes); this engine has
+    three (include/adcensus_b200.h: ADC_MAX_*).  A size beyond them must make Initialize fail -- never pass Initialize
+    and then fail Match -- and the largest accepted height must really run."""
+    import adcensus_b200 as A
+    s = A.ADCensusStereo()
+    assert s.Initialize(64, 4097, A.ADCensusOption(max_disparity=8)) is False and "height" in s.last_error
+    assert s.Initialize(64, 48, A.ADCensusOption(max_disparity=257)) is False and "disparity range" in s.last_error
+    assert s.Initialize(10001, 8, A.ADCensusOption(max_disparity=8)) is False and "width" in s.last_error
+    # a tall image above the old 2048-row limit of the median kernel, against the oracle
+    w, h, D = 24, 2100, 8
+    opt = T.default_option(max_disparity=D)
+    left, right = T.synthetic_pair(w, h, D, 21)
+    eng = _engine(w, h, opt)
+    _same("tall image", eng.match(left, right), T.Oracle(w, h, opt).match(left, right))
+    eng.close()
+
+
+def test_sync_entry_points_join_in_pipelined_mode(cone):
+    """adc_set_pipelined only changes the asynchronous entry points: a synchronous batch call on pinned buffers must
+    return with its maps complete (round-1 defect: the join was skipped for pinned buffers)."""
+    import ctypes
+    import adcensus_b200 as A
     left, right = cone
     h, w, _ = left.shape
-    plain = _engine(w, h, T.default_option(), wave_pairs=4, lanes=2)
-    want = [plain.match(left, right), plain.match(right, left)]
-    plain.close()
-    eng = _engine(w, h, T.default_option(), wave_pairs=4, lanes=2, async_refine=True)
-    n = 24
-    L = np.stack([left if i % 2 == 0 else right for i in range(n)])
-    R = np.stack([right if i % 2 == 0 else left for i in range(n)])
-    dl, dr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
-    dd = torch.zeros((n, h, w), dtype=torch.float32, device="cuda")
+    eng = _engine(w, h, T.default_option(), wave_pairs=4, lanes=3)
+    want = eng.match(left, right)
+    L = A.load_library()
+    n = 9
+    nb_img, nb_map = n * h * w * 3, n * h * w * 4
+    pl, pr, pd = L.adc_host_alloc(nb_img), L.adc_host_alloc(nb_img), L.adc_host_alloc(nb_map)
+    assert pl and pr and pd
+    al = np.ctypeslib.as_array(ctypes.cast(pl, ctypes.POINTER(ctypes.c_uint8)), (n, h, w, 3))
+    ar = np.ctypeslib.as_array(ctypes.cast(pr, ctypes.POINTER(ctypes.c_uint8)), (n, h, w, 3))
+    ad = np.ctypeslib.as_array(ctypes.cast(pd, ctypes.POINTER(ctypes.c_float)), (n, h, w))
+    al[:], ar[:] = left[None], right[None]
+    eng.set_pipelined(True)
     for _ in range(2):
-        eng.match_batch_device(n, dl.data_ptr(), dr.data_ptr(), dd.data_ptr(), torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
-    out = dd.cpu().numpy()
-    for i in range(n):
-        assert out[i].tobytes() == want[i % 2].tobytes(), f"pair {i}"
-    # the synchronous single-pair entry still works on such an engine (lane buffers, both streams idle)
-    assert eng.match(left, right).tobytes() == want[0].tobytes()
+        ad[:] = -1.0
+        assert L.adc_match_batch_strided(eng._h, n, pl, pr, pd) == 0
+        assert (ad.view(np.uint32) == want.view(np.uint32)[None]).all(), "maps incomplete on return"
+    eng.set_pipelined(False)
     eng.close()
+    for q in (pl, pr, pd):
+        L.adc_host_free(q)
+
+
+def _big():
+    import json
+    return json.loads((T.GOLDEN_DIR / "golden_big.json").read_text())
+
+
+@pytest.mark.parametrize("name", ["cloth3", "wood2", "piano"])
+def test_real_pairs_vs_reference_goldens(name):
+    """The reference's other bundled Middlebury pairs (Cloth3 view1/view5 at D = 128 is its own usage example,
+    main.cpp:30) through every stage, against sha256 hashes produced by the unmodified reference
+    (tools/make_golden_big.py): real data at D = 128, 626x555 / 653x555 / 707x481."""
+    g = _big()[name]
+    z = np.load(T.GOLDEN_DIR / "real_pairs.npz")
+    left, right = z[f"{name}_left"], z[f"{name}_right"]
+    assert [T.sha(left), T.sha(right)] == g["input_sha"]
+    h, w, _ = left.shape
+    opt = T.default_option(max_disparity=g["max_disparity"])
+    eng = _engine(w, h, opt)
+    for st in T.STAGES:
+        eng.debug_run(left, right, st)
+        for tap in T.STAGE_TAPS[st]:
+            assert T.sha(eng.tap(tap)) == g["hashes"][f"{st}/{tap}"], f"{name}: {st}/{tap}"
+    out = eng.match(left, right)
+    assert T.sha(out) == g["hashes"]["MEDIAN/DISP_L"]
+    _same(f"{name} final", out, z[f"{name}_final"])
+    # the right-view map the reference keeps private (ADCensusStereo.cpp:245-310) through the public entry point
+    assert T.sha(eng.right_disparity()) == g["hashes"]["WTA/DISP_R"]
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["kitti_s1", "kitti_s2", "p1080_s1"])
+def test_baseline_configs_vs_reference_goldens(name):
+    """BASELINE.json configs 3 and 4 (synthetic 1242x375x128, 1920x1080x192): the aggregated volume, the optimised
+    volume, both WTA maps, the outlier lists and the final map against the unmodified reference's hashes
+    (one 115 s reference run per 1080p pair, done once in the build container: tools/make_golden_big.py)."""
+    g = _big()[name]
+    w, h, D = g["width"], g["height"], g["max_disparity"]
+    seed = int(name.rsplit("_s", 1)[1])
+    left, right = T.synthetic_pair(w, h, D, seed)
+    assert [T.sha(left), T.sha(right)] == g["input_sha"]
+    eng = _engine(w, h, T.default_option(max_disparity=D))
+    out = eng.match(left, right)
+    assert T.sha(out) == g["hashes"]["MEDIAN/DISP_L"], f"{name}: final map"
+    for st, taps in (("COST", ["CENSUS_L", "VOL_INIT"]), ("ARMS", ["ARMS", "SUPCNT_H", "SUPCNT_V"]), ("AGG2", ["VOL_AGGR"]),
+                     ("AGG4", ["VOL_AGGR"]), ("SO4", ["VOL_AGGR"]), ("WTA", ["DISP_L", "DISP_R"]),
+                     ("OUTLIER", ["MISMATCHES", "OCCLUSIONS"]), ("VOTE", ["DISP_L"])):
+        eng.debug_run(left, right, st)
+        for tap in taps:
+            assert T.sha(eng.tap(tap)) == g["hashes"][f"{st}/{tap}"], f"{name}: {st}/{tap}"
+    batch = eng.match_batch(np.stack([left, left, left]), np.stack([right, right, right]))
+    assert (batch.view(np.uint32) == out.view(np.uint32)[None]).all()
+    eng.close()
+
+
+_SHARD_WORKER = r'''
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["ADC_ROOT"]); sys.path.insert(0, os.path.join(os.environ["ADC_ROOT"], "tests"))
+import adc_testlib as T
+import adcensus_b200 as A
+from adcensus_b200.parallel import run_sharded_device
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+if world > 1:
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%s" % os.environ["ADC_PORT"], rank=rank, world_size=world, device_id=dev)
+w, h, D, n = 96, 64, 32, 11
+eng = A.Engine(w, h, A.ADCensusOption(max_disparity=D), device=rank, wave_pairs=2, lanes=2)
+d_l = d_r = d_out = None
+if rank == 0:
+    pairs = [T.synthetic_pair(w, h, D, 200 + i) for i in range(n)]
+    d_l = torch.from_numpy(np.stack([p[0] for p in pairs])).to(dev)
+    d_r = torch.from_numpy(np.stack([p[1] for p in pairs])).to(dev)
+    d_out = torch.zeros((n, h, w), dtype=torch.float32, device=dev)
+for _ in range(2):          # twice: buffers and streams are reused
+    run_sharded_device(eng, d_l, d_r, d_out, n, h, w, dev)
+torch.cuda.synchronize()
+if rank == 0:
+    out = d_out.cpu().numpy()
+    orc = T.Oracle(w, h, T.default_option(max_disparity=D))
+    for i in (0, 5, 6, 10):   # both sides of the rank boundary, first and last
+        want = orc.match(*pairs[i])
+        assert out[i].tobytes() == want.tobytes(), "pair %d differs from the oracle (order or content)" % i
+    single = [eng.match(*p) for p in pairs]
+    assert all(out[i].tobytes() == single[i].tobytes() for i in range(n))
+    print("SHARD_OK")
+eng.close()
+if world > 1:
+    dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_sharded_batch_real_engine(tmp_path, world):
+    """adcensus_b200.parallel.run_sharded_device (BASELINE configs[4] form) with the REAL engine: rank 0 owns the batch,
+    NCCL scatter -> Match -> NCCL gather, order and bits against the oracle.  world = 2 needs two GPUs (gpurun --gpus 2)."""
+    import os, socket, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(_SHARD_WORKER)
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = str(sk.getsockname()[1])
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), ADC_ROOT=str(T.REPO), ADC_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=600) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-3000:]
+    assert "SHARD_OK" in outs[0][0]

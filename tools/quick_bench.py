@@ -29,9 +29,9 @@ for S, lanes in cfgs:
     e1.record(st)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    print(f"vote_mode={os.environ.get('ADC_VOTE_MODE','-')} S={S} lanes={lanes}: {n} pairs in {ms:.2f} ms -> {n / ms * 1000:.1f} maps/s", flush=True)
+    print(f"S={S} lanes={lanes}: {n} pairs in {ms:.2f} ms -> {n / ms * 1000:.1f} maps/s", flush=True)
     if (S, lanes) == cfgs[0]:
-        for name in ("cost_volume", "arm_sum_h", "arm_sum_v_div", "scanline_x", "scanline_y", "wta"):
+        for name in ("cost_volume", "arm_sum_h", "arm_sum2_v", "arm_sum2_h", "arm_sum_h_div", "scanline_x", "scanline_y", "wta"):
             kms, kb = eng.profile_kernel(name, 5)
             print(f"   kernel {name:14s} {kms*1000:8.1f} us per wave of {S}  -> {kb/kms/1e6:8.1f} GB/s algorithmic")
     eng.close()
@@ -41,7 +41,7 @@ if os.environ.get("ADC_SWEEP_S"):
         eng.match_batch_device(S, dl.data_ptr(), dr.data_ptr(), dd.data_ptr(), torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         line = f"S={S}: per-pair us:"
-        for name in ("cost_volume", "arm_sum_h", "arm_sum_v_div", "scanline_x", "scanline_y", "wta"):
+        for name in ("cost_volume", "arm_sum_h", "arm_sum2_v", "arm_sum2_h", "arm_sum_h_div", "scanline_x", "scanline_y", "wta"):
             kms, kb = eng.profile_kernel(name, 10)
             line += f" {name}={kms*1000/S:.1f}"
         print(line, flush=True)
