@@ -128,6 +128,7 @@ bool adc_arm_sum2_available(const AdcParams& P);
 bool adc_launch_arm_sum2(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int dir,
                          const uint16_t* sup_mid, cudaStream_t st, unsigned long long* launches);
 size_t adc_arm_rec_bytes(const AdcDims& dm, int L1);   // window records of one pair
+size_t adc_arm_overread_floats(const AdcDims& dm);     // padding the arena keeps behind the two volumes
 void adc_launch_so_bitrows(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
 size_t adc_so_rec_bytes(const AdcDims& dm);
 size_t adc_so_bitrow_bytes(const AdcDims& dm);

@@ -112,6 +112,7 @@ size_t carve_lane(void* base, const AdcDims& dm, int L1, int S, AdcWave* w) {
     AdcWave t{};
     t.volA = c.take<float>((size_t)S * dm.vol_stride);
     t.volB = c.take<float>((size_t)S * dm.vol_stride);
+    c.take<float>(adc_arm_overread_floats(dm));           // the arm-sum walks may load (never use) a few taps past a volume's end
     t.bgr = c.take<uint8_t>((size_t)S * 2 * N * 3);
     t.gray = c.take<uint8_t>((size_t)S * 2 * N);
     t.bgrx = c.take<unsigned>((size_t)S * 2 * N);

@@ -171,8 +171,29 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-template <int K, int LPS, bool FULL, bool CT = false>   // FULL: D == LPS*K, every lane's K values are real disparities (no padding logic)
-                                                        // CT (experimental, ADC_SO_CT=1, needs FULL): strides and chunk counts as compile-time constants
+// Bulk asynchronous copies (the TMA engine's 1-D form, cp.async.bulk) completing on an mbarrier: ONE instruction moves a
+// pixel's whole cost vector into the ring slot, where the cp.async form needs Dp/4 16-byte copies spread over the lanes.
+__device__ __forceinline__ unsigned so_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+template <int K, int LPS, bool FULL, bool BULK>   // FULL: D == LPS*K, every lane's K values are real disparities (no padding logic)
+                                                  // BULK: ring slots filled by cp.async.bulk + mbarrier (one lane per line issues), else by cp.async
 __global__ void __launch_bounds__(SO_WARPS * 32)
 k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
            const unsigned* __restrict__ rec, int sx, int sy) {
@@ -186,12 +207,22 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
     const int pair = blockIdx.y;
     const int n_lines = sx ? dm.H : dm.W, n_steps = sx ? dm.W : dm.H;
     const bool live = line < n_lines;            // dead groups run along (uniform control flow) but move no data
-    const int W = dm.W, D = (FULL && CT) ? K * LPS : dm.D, Dp = (FULL && CT) ? K * LPS : dm.Dp;   // (FULL: D == Dp == K*LPS)
+    const int W = dm.W, D = dm.D, Dp = dm.Dp;
     const int pstep = sx + sy * W;               // signed pixel stride along the path
     const int nrec = so_rec_words(Dp);
     const int cost_chunks = Dp >> 2, rec_chunks = nrec >> 2;      // 16-byte chunks per step
     const int slot_bytes = (Dp + nrec) * 4;
     unsigned char* ring = so_smem + (size_t)((wid * LPW + sub) * PF) * slot_bytes;
+    // BULK: one mbarrier per ring slot, behind the rings of all the CTA's lines
+    const unsigned bar0 = so_smem_u32(so_smem + (size_t)SO_WARPS * LPW * PF * slot_bytes) + (unsigned)((wid * LPW + sub) * PF) * 8u;
+    if (BULK) {
+        if (gl == 0) {
+#pragma unroll
+            for (int j = 0; j < PF; j++) mbar_init(bar0 + 8u * j, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     const float* S = src + (size_t)pair * dm.vol_stride;
     float* O = dst + (size_t)pair * dm.vol_stride;
     const int variant = sx ? (sx > 0 ? 0 : 1) : (sy > 0 ? 2 : 3);
@@ -207,8 +238,17 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
         const long long p = (long long)y0 * W + x0 + (long long)step * pstep;
         unsigned char* slot = ring + (size_t)(step % PF) * slot_bytes;
         const float* cs = S + (size_t)p * Dp;
-        for (int c = gl; c < cost_chunks; c += LPS) cp_async16(slot + c * 16, cs + c * 4);
         const unsigned* rs = R + (size_t)p * nrec;
+        if (BULK) {
+            if (gl == 0) {           // the slot's previous contents were read by every lane before the __syncwarp preceding this call
+                const unsigned bar = bar0 + 8u * (unsigned)(step % PF), dst = so_smem_u32(slot);
+                mbar_expect_tx(bar, (unsigned)slot_bytes);
+                bulk_g2s(dst, cs, (unsigned)(Dp * 4), bar);
+                bulk_g2s(dst + (unsigned)(Dp * 4), rs, (unsigned)(nrec * 4), bar);
+            }
+            return;
+        }
+        for (int c = gl; c < cost_chunks; c += LPS) cp_async16(slot + c * 16, cs + c * 4);
         for (int c = gl; c < rec_chunks; c += LPS) cp_async16(slot + Dp * 4 + c * 16, rs + c * 4);
     };
 
@@ -220,7 +260,7 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
 #pragma unroll
     for (int j = 1; j <= PF; j++) {
         if (j < n_steps) prefetch(j);
-        cp_async_commit();           // one group per step, empty groups keep the count uniform
+        if (!BULK) cp_async_commit();   // one group per step, empty groups keep the count uniform
     }
     float L[K];
     {
@@ -243,8 +283,12 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
 
     const int bit0 = gl * K;   // first disparity of this lane inside the record's bit string
     for (int step = 1; step < n_steps; step++) {
-        cp_async_wait<PF - 1>();     // the group of `step` has landed (for this lane's copies)
-        __syncwarp();                // ... and for every other lane's
+        if (BULK) {                  // the k-th use of a slot completes phase k of its mbarrier: steps step, step + PF, ...
+            if (live) mbar_wait(bar0 + 8u * (unsigned)(step % PF), (unsigned)((step / PF - (step % PF == 0 ? 1 : 0)) & 1));
+        } else {
+            cp_async_wait<PF - 1>(); // the group of `step` has landed (for this lane's copies)
+            __syncwarp();            // ... and for every other lane's
+        }
         const unsigned char* slot = ring + (size_t)(step % PF) * slot_bytes;
         float C[K];
         ld_vec<K>(reinterpret_cast<const float*>(slot), gl, Dp, C);
@@ -253,7 +297,7 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
         const unsigned bits = __funnelshift_r(rw[1 + (bit0 >> 5)], rw[2 + (bit0 >> 5)], bit0 & 31);
         __syncwarp();                // everyone has read the slot before it is refilled
         if (step + PF < n_steps) prefetch(step + PF);
-        cp_async_commit();
+        if (!BULK) cp_async_commit();
         pi += pstep;
 
         const float up = __shfl_up_sync(0xffffffffu, L[K - 1], 1, LPS);
@@ -287,35 +331,36 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
         for (int o = LPS / 2; o >= 1; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         minL = mn;
     }
-    cp_async_wait<0>();
+    if (!BULK) cp_async_wait<0>();
 }
 
-template <int K, int LPS, bool FULL, bool CT = false>
+template <int K, int LPS, bool FULL, bool BULK>
 static int launch_scanline_kf(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
                              cudaStream_t st) {
     constexpr int LPW = 32 / LPS;
     const int n_lines = sx ? P.dm.H : P.dm.W;
     const int slot_bytes = (P.dm.Dp + so_rec_words(P.dm.Dp)) * 4;
-    const size_t smem = (size_t)SO_WARPS * LPW * SO_PF * slot_bytes;
+    const size_t smem = (size_t)SO_WARPS * LPW * SO_PF * (slot_bytes + (BULK ? 8 : 0));
     static AdcOnce attr_once;
     if (adc_once_needed(attr_once)) {
-        cudaFuncSetAttribute(k_scanline<K, LPS, FULL, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_scanline<K, LPS, FULL, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         adc_once_done(attr_once);
     }
     const int lines_per_block = SO_WARPS * LPW;
     dim3 grid((n_lines + lines_per_block - 1) / lines_per_block, w.S);
-    k_scanline<K, LPS, FULL, CT><<<grid, SO_WARPS * 32, smem, st>>>(P, src, dst, w.so_rec, sx, sy);
+    k_scanline<K, LPS, FULL, BULK><<<grid, SO_WARPS * 32, smem, st>>>(P, src, dst, w.so_rec, sx, sy);
     return 0;
 }
 
 template <int K, int LPS>
 static int launch_scanline_k(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
                              cudaStream_t st) {
-    static int ct = -1;   // ADC_SO_CT=1: compile-time strides for the exact-fit instantiation (not validated on a GPU yet)
-    if (ct < 0) { const char* m = getenv("ADC_SO_CT"); ct = m ? atoi(m) : 0; }
-    if (P.dm.D == K * LPS && P.dm.Dp == K * LPS && ct && K == 8 && LPS == 8) return launch_scanline_kf<K, LPS, true, (K == 8 && LPS == 8)>(P, w, src, dst, sx, sy, st);
-    if (P.dm.D == K * LPS) return launch_scanline_kf<K, LPS, true>(P, w, src, dst, sx, sy, st);
-    return launch_scanline_kf<K, LPS, false>(P, w, src, dst, sx, sy, st);
+    static int bulk = -1;   // development switch ADC_SO_BULK=0: ring slots filled by per-lane cp.async instead of cp.async.bulk
+    if (bulk < 0) { const char* m = getenv("ADC_SO_BULK"); bulk = m ? atoi(m) : 1; }
+    if (P.dm.D == K * LPS) return bulk ? launch_scanline_kf<K, LPS, true, true>(P, w, src, dst, sx, sy, st)
+                                       : launch_scanline_kf<K, LPS, true, false>(P, w, src, dst, sx, sy, st);
+    return bulk ? launch_scanline_kf<K, LPS, false, true>(P, w, src, dst, sx, sy, st)
+                : launch_scanline_kf<K, LPS, false, false>(P, w, src, dst, sx, sy, st);
 }
 
 void adc_launch_so_bitrows(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {
@@ -332,11 +377,6 @@ int adc_launch_scanline(const AdcParams& P, const AdcWave& w, const float* src, 
     const int Dp = P.dm.Dp;
     int rc = 1;
 #define SO_GO(KK, LL) rc = launch_scanline_k<KK, LL>(P, w, src, dst, sx, sy, st)
-    static int lps = -1;       // ADC_SO_LPS=16: sixteen lanes per line also for Dp <= 64 (twice the warps, half the values per lane)
-    if (lps < 0) { const char* m = getenv("ADC_SO_LPS"); lps = m ? atoi(m) : 0; }
-    if (lps == 16 && Dp <= 64 && Dp > 32) {
-        switch ((Dp + 15) / 16) { case 3: SO_GO(3, 16); break; default: SO_GO(4, 16); }
-    } else
     if (Dp <= 64) {            // 8 lanes per line
         switch ((Dp + 7) / 8) { case 1: SO_GO(1, 8); break; case 2: SO_GO(2, 8); break; case 3: SO_GO(3, 8); break; case 4: SO_GO(4, 8); break;
                                 case 5: SO_GO(5, 8); break; case 6: SO_GO(6, 8); break; case 7: SO_GO(7, 8); break; default: SO_GO(8, 8); }

@@ -13,35 +13,26 @@ __device__ __forceinline__ float adc_subpixel(float c1, float c2, float cmin, in
 // ---------------------------------------------------------------------------------------------
 // One kernel, both views, any disparity range.  A CTA owns WT_PX neighbouring pixels of one image row -- as pixels of
 // the left view AND as pixels of the right view -- and sweeps the disparity range in chunks of WT_DC.  Per chunk two
-// small tiles are staged in shared memory (coalesced 128-bit loads, 128 contiguous bytes per column):
+// small tiles are staged in shared memory (coalesced 128-bit loads, all of a thread's loads in flight before the first
+// store):
 //   left tile   L[t][k] = cost(x0 + t, d0 + k)                          the chunk of the CTA's own columns
 //   right tile  R[k][r] = cost(x0 + r + dmin + d0 + k, d0 + k)          cost_R(xr, d) = cost_L(xr + d, d) (:262-287),
 //                                                                       stored skewed: the diagonal a right pixel walks is a
 //                                                                       column of R, Large_Float where the column is outside
 // and every thread scans its two chunk vectors sequentially with the reference's strict '>' (first minimum wins),
-// carrying (minimum, argmin, the two parabola neighbours, the previous cost) in registers from chunk to chunk.
-// A column outside the image is Large_Float: never the minimum (the running minimum starts there), and exactly what the
-// reference's cost_local holds for the parabola (:277-286).  Shared memory per CTA is independent of the disparity
-// range (33 KB), so the kernel keeps its six CTAs per SM at D = 64 as at D = 256 -- the first version staged
-// (WT_PX + D - 1) whole columns, 172 KB for a 64-thread CTA at D = 192.
+// carrying (minimum, argmin) in registers from chunk to chunk: three instructions per cost.  A column outside the image
+// is Large_Float: never the minimum (the running minimum starts there).  The two parabola neighbours of each minimum
+// are fetched afterwards (four L2 hits per pixel), Large_Float where the reference's cost_local holds it (:277-286).
+// Shared memory per CTA is independent of the disparity range (17 KB), so the kernel keeps eight CTAs per SM at D = 64
+// as at D = 256 -- the first version staged (WT_PX + D - 1) whole columns, 172 KB for a 64-thread CTA at D = 192.
 // The right tile's columns are the left tile of the neighbouring CTAs: they come out of L2.
 // ---------------------------------------------------------------------------------------------
 #define WT_PX 128
-#define WT_DC 32
+#define WT_DC 16
 #define WT_LS (WT_DC + 1)      // row stride of the left tile (odd: thread t walks bank t + k)
+#define WT_RT ((WT_PX + WT_DC - 1 + WT_PX / 4 - 1) / (WT_PX / 4))   // staging trips of the right tile (32 columns per trip)
 
-struct WtaRun {                // running state of one view's scan
-    float best, c1, c2, prev;
-    int bd;                    // argmin as index d - dmin; -2 = none yet (so that "bd + 1" never matches)
-};
-
-__device__ __forceinline__ void wta_step(WtaRun& s, float c, int di) {
-    if (di == s.bd + 1) s.c2 = c;                       // the cost right after the current minimum
-    if (s.best > c) { s.best = c; s.bd = di; s.c1 = s.prev; }
-    s.prev = c;
-}
-
-__global__ void __launch_bounds__(WT_PX)
+__global__ void __launch_bounds__(WT_PX, 8)
 k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, float* __restrict__ disp_r) {
     __shared__ float tl[WT_PX * WT_LS];
     __shared__ float tr[WT_DC * WT_PX];
@@ -49,54 +40,62 @@ k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, flo
     const int W = dm.W, D = dm.D, Dp = dm.Dp;
     const float* rowv = vol + (size_t)pair * dm.vol_stride + (size_t)y * W * Dp;
     const int t = threadIdx.x;
-    const int kq = t & 7, cj = t >> 3;                  // staging role: float4 kq of the chunk, 16 columns per trip
-    WtaRun sl, sr;
-    sl.best = sr.best = ADC_LARGE_F;                    // min_cost starts at Large_Float (:209, :266)
-    sl.c1 = sl.c2 = sr.c1 = sr.c2 = ADC_LARGE_F;
-    sl.prev = sr.prev = ADC_LARGE_F;
-    sl.bd = sr.bd = -2;
+    const int kq = t & 3, cj = t >> 2;                  // staging role: float4 kq of the chunk, 32 columns per trip
+    const float4 LARGE4 = make_float4(ADC_LARGE_F, ADC_LARGE_F, ADC_LARGE_F, ADC_LARGE_F);
+    float lbest = ADC_LARGE_F, rbest = ADC_LARGE_F;     // min_cost starts at Large_Float (:209, :266)
+    int lbd = -1, rbd = -1;                             // argmin as index d - dmin, -1 = none yet
     for (int d0 = 0; d0 < D; d0 += WT_DC) {
         const int dn = min(WT_DC, D - d0);
         const bool qin = d0 + 4 * kq < Dp;              // this float4 exists (Dp is a multiple of 4)
-        // ---- left tile: columns x0 .. x0 + WT_PX - 1
-#pragma unroll 4
-        for (int c = cj; c < WT_PX; c += WT_PX / 8) {
-            const int x = x0 + c;
-            float4 v = make_float4(ADC_LARGE_F, ADC_LARGE_F, ADC_LARGE_F, ADC_LARGE_F);
-            if (qin && x < W) v = __ldg(reinterpret_cast<const float4*>(rowv + (size_t)x * Dp + d0) + kq);
-            float* o = tl + c * WT_LS + 4 * kq;
-            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-        }
-        // ---- right tile: column j of the tile is image column cb + j; its element k belongs to right pixel r = j - k
-        const int cb = x0 + dm.dmin + d0;
-#pragma unroll 4
-        for (int j = cj; j < WT_PX + WT_DC - 1; j += WT_PX / 8) {
-            const int x = cb + j;
-            float4 v = make_float4(ADC_LARGE_F, ADC_LARGE_F, ADC_LARGE_F, ADC_LARGE_F);
-            if (qin && x >= 0 && x < W) v = __ldg(reinterpret_cast<const float4*>(rowv + (size_t)x * Dp + d0) + kq);
-            const float e[4] = {v.x, v.y, v.z, v.w};
+        const float* cv = rowv + d0 + 4 * kq;
+        const int cb = x0 + dm.dmin + d0;               // image column of column 0 of the right tile
+        float4 vl[WT_PX / 32], vr[WT_RT];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int k = 4 * kq + i, r = j - k;
-                if (r >= 0 && r < WT_PX) tr[k * WT_PX + r] = e[i];
+        for (int i = 0; i < WT_PX / 32; i++) {          // left tile: columns x0 .. x0 + WT_PX - 1
+            const int x = x0 + cj + 32 * i;
+            vl[i] = (qin && x < W) ? __ldg(reinterpret_cast<const float4*>(cv + x * Dp)) : LARGE4;
+        }
+#pragma unroll
+        for (int i = 0; i < WT_RT; i++) {               // right tile: column j of the tile is image column cb + j
+            const int j = cj + 32 * i, x = cb + j;
+            vr[i] = (qin && j < WT_PX + WT_DC - 1 && x >= 0 && x < W) ? __ldg(reinterpret_cast<const float4*>(cv + x * Dp)) : LARGE4;
+        }
+#pragma unroll
+        for (int i = 0; i < WT_PX / 32; i++) {
+            float* o = tl + (cj + 32 * i) * WT_LS + 4 * kq;
+            o[0] = vl[i].x; o[1] = vl[i].y; o[2] = vl[i].z; o[3] = vl[i].w;
+        }
+#pragma unroll
+        for (int i = 0; i < WT_RT; i++) {               // element k of tile column j belongs to right pixel r = j - k
+            const int r0 = cj + 32 * i - 4 * kq;
+            const float e[4] = {vr[i].x, vr[i].y, vr[i].z, vr[i].w};
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int r = r0 - c;
+                if (r >= 0 && r < WT_PX) tr[(4 * kq + c) * WT_PX + r] = e[c];
             }
         }
         __syncthreads();
-        // ---- scans: thread t = left pixel x0 + t and right pixel x0 + t
+        // ---- scans: thread t = left pixel x0 + t and right pixel x0 + t; indices relative to the chunk
         const float* pl = tl + t * WT_LS;
         const float* pr = tr + t;
+        int lk = -1, rk = -1;
         if (dn == WT_DC) {
-#pragma unroll 8
+#pragma unroll
             for (int k = 0; k < WT_DC; k++) {
-                wta_step(sl, pl[k], d0 + k);
-                wta_step(sr, pr[k * WT_PX], d0 + k);
+                const float a = pl[k], b = pr[k * WT_PX];
+                if (lbest > a) { lbest = a; lk = k; }
+                if (rbest > b) { rbest = b; rk = k; }
             }
         } else {
             for (int k = 0; k < dn; k++) {
-                wta_step(sl, pl[k], d0 + k);
-                wta_step(sr, pr[k * WT_PX], d0 + k);
+                const float a = pl[k], b = pr[k * WT_PX];
+                if (lbest > a) { lbest = a; lk = k; }
+                if (rbest > b) { rbest = b; rk = k; }
             }
         }
+        if (lk >= 0) lbd = d0 + lk;
+        if (rk >= 0) rbd = d0 + rk;
         __syncthreads();
     }
     const int x = x0 + t;
@@ -104,15 +103,25 @@ k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, flo
     const size_t o = (size_t)pair * dm.N + (size_t)y * W + x;
     {   // left view: a minimum at either end of the range (or none) is Invalid (ADCensusStereo.cpp:224-227)
         float out = ADC_INVALID_F;
-        if (sl.bd > 0 && sl.bd < D - 1) out = adc_subpixel(sl.c1, sl.c2, sl.best, dm.dmin + sl.bd);
+        if (lbd > 0 && lbd < D - 1) {
+            const float* v = rowv + x * Dp + lbd;
+            out = adc_subpixel(__ldg(v - 1), __ldg(v + 1), lbest, dm.dmin + lbd);
+        }
         disp_l[o] = out;
     }
     {   // right view: a minimum at either end gives the integer disparity, not Invalid (:290-293); `best` starts at 0
-        // (not dmin) when no column was valid, as in the reference (:271)
+        // (not dmin) when no column was valid, as in the reference (:271); a parabola neighbour whose column lies
+        // outside the image is Large_Float (:277-286)
         float out = 0.0f;
-        if (sr.bd >= 0) {
-            const int best = dm.dmin + sr.bd;
-            out = (sr.bd > 0 && sr.bd < D - 1) ? adc_subpixel(sr.c1, sr.c2, sr.best, best) : (float)best;
+        if (rbd >= 0) {
+            const int best = dm.dmin + rbd;
+            out = (float)best;
+            if (rbd > 0 && rbd < D - 1) {
+                const int x1 = x + best - 1, x2 = x + best + 1;
+                const float c1 = (x1 >= 0 && x1 < W) ? __ldg(rowv + x1 * Dp + rbd - 1) : ADC_LARGE_F;
+                const float c2 = (x2 >= 0 && x2 < W) ? __ldg(rowv + x2 * Dp + rbd + 1) : ADC_LARGE_F;
+                out = adc_subpixel(c1, c2, rbest, best);
+            }
         }
         disp_r[o] = out;
     }
