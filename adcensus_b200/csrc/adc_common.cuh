@@ -74,6 +74,9 @@ inline void adc_once_done(AdcOnce& o) {
     o.done[dev & 63].store(1, std::memory_order_release);
 }
 
+// TMA descriptors (CUtensorMap, 128 bytes each) of a lane's two cost volumes for the two axes of the fused aggregation kernel
+struct alignas(64) AdcArmTmaps { unsigned char map[2][2][128]; int ok; };
+
 // ---- launchers (defined in the k_*.cu files; all asynchronous on `st`) -------------------------
 struct AdcWave {            // device pointers of one wave (S pairs)
     int S;                  // active pairs in this launch
@@ -83,6 +86,7 @@ struct AdcWave {            // device pointers of one wave (S pairs)
     unsigned long long* census; // [S][2][N]
     float* volA; float* volB;
     uchar4* arms;
+    const AdcArmTmaps* arm_tm;   // host memory, owned by the lane (NULL: the fused kernel loads its source with LDG)
     unsigned* arm_rec;      // [S][window records of both axes] which of a group's four outputs takes which tap (k_aggregate.cu)
     uint16_t* sup_h; uint16_t* sup_v;
     uint8_t* dmap;          // [S][4][N]: 0 = left-horizontal, 1 = left-vertical, 2 = right-horizontal, 3 = right-vertical
@@ -128,6 +132,7 @@ bool adc_arm_sum2_available(const AdcParams& P);
 bool adc_launch_arm_sum2(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int dir,
                          const uint16_t* sup_mid, cudaStream_t st, unsigned long long* launches);
 size_t adc_arm_rec_bytes(const AdcDims& dm, int L1);   // window records of one pair
+bool adc_arm_tmaps_encode(const AdcParams& P, int S, float* volA, float* volB, AdcArmTmaps* out);   // false: TMA path not available
 size_t adc_arm_overread_floats(const AdcDims& dm);     // padding the arena keeps behind the two volumes
 void adc_launch_so_bitrows(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches);
 size_t adc_so_rec_bytes(const AdcDims& dm);

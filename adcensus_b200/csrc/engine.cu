@@ -55,6 +55,7 @@ struct Lane {
     cudaEvent_t ev_in_free = nullptr;  // the H2D of the latest wave has consumed the staging-in buffer
     void* arena = nullptr;
     AdcWave w{};                       // device pointers, capacity S pairs
+    AdcArmTmaps arm_tm{};              // TMA descriptors of this lane's volumes (fused aggregation kernel)
     uint8_t* pin_in = nullptr;         // [S][2][N*3] pinned staging (pageable callers only)
     float* pin_out = nullptr;          // [S][N]
     // pending copy-out of a staged wave (pageable callers)
@@ -550,6 +551,7 @@ int adc_create(int32_t width, int32_t height, const adc_option* opt, const adc_c
         const size_t bytes = carve_lane(nullptr, e->P.dm, e->P.L1, S, nullptr);
         if (cudaMalloc(&ln.arena, bytes) != cudaSuccess) { cudaGetLastError(); return bail(fail(ADC_ERR_NOMEM, "device arena of %zu bytes", bytes)); }
         carve_lane(ln.arena, e->P.dm, e->P.L1, S, &ln.w);
+        if (adc_arm_tmaps_encode(e->P, S, ln.w.volA, ln.w.volB, &ln.arm_tm)) ln.w.arm_tm = &ln.arm_tm;
         if (cudaMemsetAsync(ln.arena, 0, bytes, ln.st) != cudaSuccess) return bail(fail(ADC_ERR_CUDA, "memset failed"));
         if (cudaHostAlloc((void**)&ln.pin_in, (size_t)S * 2 * N * 3, cudaHostAllocDefault) != cudaSuccess ||
             cudaHostAlloc((void**)&ln.pin_out, (size_t)S * N * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {

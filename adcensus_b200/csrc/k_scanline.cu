@@ -185,10 +185,11 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    unsigned ok;
+    unsigned ok, spins = 0;
     do {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 24)) __trap();   // a copy that never completes is a bug: fail the launch instead of hanging the device
     } while (!ok);
 }
 
@@ -212,17 +213,10 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
     const int nrec = so_rec_words(Dp);
     const int cost_chunks = Dp >> 2, rec_chunks = nrec >> 2;      // 16-byte chunks per step
     const int slot_bytes = (Dp + nrec) * 4;
-    unsigned char* ring = so_smem + (size_t)((wid * LPW + sub) * PF) * slot_bytes;
-    // BULK: one mbarrier per ring slot, behind the rings of all the CTA's lines
-    const unsigned bar0 = so_smem_u32(so_smem + (size_t)SO_WARPS * LPW * PF * slot_bytes) + (unsigned)((wid * LPW + sub) * PF) * 8u;
-    if (BULK) {
-        if (gl == 0) {
-#pragma unroll
-            for (int j = 0; j < PF; j++) mbar_init(bar0 + 8u * j, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
-    }
+    // Ring: PF slots per WARP; a slot holds the cost vectors of the warp's LPW lines back to back, then their records, so
+    // that for the +-y passes (the lines are adjacent columns = adjacent memory) ONE bulk copy fills all of them.
+    unsigned char* wring = so_smem + (size_t)(wid * PF) * LPW * slot_bytes;
+    const int cost_off = sub * Dp * 4, rec_off = LPW * Dp * 4 + sub * nrec * 4;    // this line's part of a slot
     const float* S = src + (size_t)pair * dm.vol_stride;
     float* O = dst + (size_t)pair * dm.vol_stride;
     const int variant = sx ? (sx > 0 ? 0 : 1) : (sy > 0 ? 2 : 3);
@@ -232,24 +226,50 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
     const int y0 = sy ? (sy > 0 ? 0 : dm.H - 1) : line;
     long long pi = (long long)y0 * W + x0;
     if (!live) pi = 0;
+    const int line0 = (blockIdx.x * SO_WARPS + wid) * LPW;                        // first line of this warp
+    const int nlive = min(LPW, max(0, n_lines - line0));                          // its lines that exist
+    // BULK: one mbarrier per (warp, slot), behind the rings of all warps
+    const unsigned bar0 = so_smem_u32(so_smem + (size_t)SO_WARPS * PF * LPW * slot_bytes) + (unsigned)(wid * PF) * 8u;
+    if (BULK) {
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < PF; j++) mbar_init(bar0 + 8u * j, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+
+    // BULK producers: for the +-y passes lane 0 fills the whole slot with two copies (the warp's lines are adjacent columns);
+    // for the +-x passes lane l fills line l's part (its lines are different image rows).  Each keeps the addresses of the
+    // NEXT step to fetch and advances them by a constant -- prefetch() is called for consecutive steps 1, 2, 3, ...
+    const bool producer = BULK && nlive > 0 && (sy ? lane == 0 : lane < nlive);
+    const int pline = sy ? 0 : lane;                                              // producer lane -> line of the warp
+    const long long pp1 = sy ? ((long long)y0 + sy) * W + line0 : (long long)(line0 + pline) * W + x0 + sx;   // its pixel at step 1
+    const float* pcs = S + (producer ? (size_t)pp1 * Dp : 0);
+    const unsigned* prs = R + (producer ? (size_t)pp1 * nrec : 0);
+    const long long dcs = (long long)pstep * Dp, drs = (long long)pstep * nrec;
+    const unsigned pb_c = (unsigned)((sy ? nlive : 1) * Dp * 4), pb_r = (unsigned)((sy ? nlive : 1) * nrec * 4);
+    const unsigned po_c = (unsigned)(pline * Dp * 4), po_r = (unsigned)(LPW * Dp * 4 + pline * nrec * 4);
 
     auto prefetch = [&](int step) {   // issue the copies of `step` into its ring slot (no commit)
-        if (!live) return;
-        const long long p = (long long)y0 * W + x0 + (long long)step * pstep;
-        unsigned char* slot = ring + (size_t)(step % PF) * slot_bytes;
-        const float* cs = S + (size_t)p * Dp;
-        const unsigned* rs = R + (size_t)p * nrec;
-        if (BULK) {
-            if (gl == 0) {           // the slot's previous contents were read by every lane before the __syncwarp preceding this call
-                const unsigned bar = bar0 + 8u * (unsigned)(step % PF), dst = so_smem_u32(slot);
-                mbar_expect_tx(bar, (unsigned)slot_bytes);
-                bulk_g2s(dst, cs, (unsigned)(Dp * 4), bar);
-                bulk_g2s(dst + (unsigned)(Dp * 4), rs, (unsigned)(nrec * 4), bar);
+        unsigned char* slot = wring + (size_t)(step % PF) * LPW * slot_bytes;
+        if (BULK) {   // (the slot's previous contents were read by every lane before the __syncwarp preceding this call)
+            const unsigned bar = bar0 + 8u * (unsigned)(step % PF), dst0 = so_smem_u32(slot);
+            if (lane == 0 && nlive > 0) mbar_expect_tx(bar, (unsigned)(nlive * slot_bytes));
+            if (!sy) __syncwarp();          // the transaction count is armed before another lane's copy can complete on it
+            if (producer) {
+                bulk_g2s(dst0 + po_c, pcs, pb_c, bar);
+                bulk_g2s(dst0 + po_r, prs, pb_r, bar);
+                pcs += dcs; prs += drs;
             }
             return;
         }
-        for (int c = gl; c < cost_chunks; c += LPS) cp_async16(slot + c * 16, cs + c * 4);
-        for (int c = gl; c < rec_chunks; c += LPS) cp_async16(slot + Dp * 4 + c * 16, rs + c * 4);
+        if (!live) return;
+        const long long p = (long long)y0 * W + x0 + (long long)step * pstep;
+        const float* cs = S + (size_t)p * Dp;
+        const unsigned* rs = R + (size_t)p * nrec;
+        for (int c = gl; c < cost_chunks; c += LPS) cp_async16(slot + cost_off + c * 16, cs + c * 4);
+        for (int c = gl; c < rec_chunks; c += LPS) cp_async16(slot + rec_off + c * 16, rs + c * 4);
     };
 
     bool valid[K];
@@ -284,15 +304,15 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
     const int bit0 = gl * K;   // first disparity of this lane inside the record's bit string
     for (int step = 1; step < n_steps; step++) {
         if (BULK) {                  // the k-th use of a slot completes phase k of its mbarrier: steps step, step + PF, ...
-            if (live) mbar_wait(bar0 + 8u * (unsigned)(step % PF), (unsigned)((step / PF - (step % PF == 0 ? 1 : 0)) & 1));
+            if (nlive > 0) mbar_wait(bar0 + 8u * (unsigned)(step % PF), (unsigned)((step / PF - (step % PF == 0 ? 1 : 0)) & 1));
         } else {
             cp_async_wait<PF - 1>(); // the group of `step` has landed (for this lane's copies)
             __syncwarp();            // ... and for every other lane's
         }
-        const unsigned char* slot = ring + (size_t)(step % PF) * slot_bytes;
+        const unsigned char* slot = wring + (size_t)(step % PF) * LPW * slot_bytes;
         float C[K];
-        ld_vec<K>(reinterpret_cast<const float*>(slot), gl, Dp, C);
-        const unsigned* rw = reinterpret_cast<const unsigned*>(slot + Dp * 4);
+        ld_vec<K>(reinterpret_cast<const float*>(slot + cost_off), gl, Dp, C);
+        const unsigned* rw = reinterpret_cast<const unsigned*>(slot + rec_off);
         const bool a1 = rw[0] != 0u;
         const unsigned bits = __funnelshift_r(rw[1 + (bit0 >> 5)], rw[2 + (bit0 >> 5)], bit0 & 31);
         __syncwarp();                // everyone has read the slot before it is refilled
@@ -340,7 +360,7 @@ static int launch_scanline_kf(const AdcParams& P, const AdcWave& w, const float*
     constexpr int LPW = 32 / LPS;
     const int n_lines = sx ? P.dm.H : P.dm.W;
     const int slot_bytes = (P.dm.Dp + so_rec_words(P.dm.Dp)) * 4;
-    const size_t smem = (size_t)SO_WARPS * LPW * SO_PF * (slot_bytes + (BULK ? 8 : 0));
+    const size_t smem = (size_t)SO_WARPS * SO_PF * ((size_t)LPW * slot_bytes + (BULK ? 8 : 0));
     static AdcOnce attr_once;
     if (adc_once_needed(attr_once)) {
         cudaFuncSetAttribute(k_scanline<K, LPS, FULL, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
