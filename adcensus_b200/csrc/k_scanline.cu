@@ -253,7 +253,7 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
 
     auto prefetch = [&](int step) {   // issue the copies of `step` into its ring slot (no commit)
         unsigned char* slot = wring + (size_t)(step % PF) * LPW * slot_bytes;
-        if (BULK) {   // (the slot's previous contents were read by every lane before the __syncwarp preceding this call)
+        if (BULK) {   // (the slot's previous contents were read, and fenced against the async proxy, by every lane before the __syncwarp preceding this call)
             const unsigned bar = bar0 + 8u * (unsigned)(step % PF), dst0 = so_smem_u32(slot);
             if (lane == 0 && nlive > 0) mbar_expect_tx(bar, (unsigned)(nlive * slot_bytes));
             if (!sy) __syncwarp();          // the transaction count is armed before another lane's copy can complete on it
@@ -315,7 +315,11 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
         const unsigned* rw = reinterpret_cast<const unsigned*>(slot + rec_off);
         const bool a1 = rw[0] != 0u;
         const unsigned bits = __funnelshift_r(rw[1 + (bit0 >> 5)], rw[2 + (bit0 >> 5)], bit0 & 31);
-        __syncwarp();                // everyone has read the slot before it is refilled
+        // Everyone has read the slot before it is refilled.  The refill of a BULK ring is a write of the ASYNC proxy (the
+        // TMA engine), the reads above went through the generic proxy: each lane orders its reads against that proxy
+        // before the barrier -- without the proxy fence about one pair in four of a loaded GPU came out wrong.
+        if (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
         if (step + PF < n_steps) prefetch(step + PF);
         if (!BULK) cp_async_commit();
         pi += pstep;
@@ -372,11 +376,18 @@ static int launch_scanline_kf(const AdcParams& P, const AdcWave& w, const float*
     return 0;
 }
 
+// Which way a pass fills its ring (measured on B200, wave of 32 Cone pairs / KITTI shape / 1080p):
+//   +-y passes: the warp's lines are adjacent columns, one bulk copy (+ one for the records) fills the whole slot -- 543 us
+//               against 571 us with per-lane cp.async (Cone), 6.30 against 6.82 ms (1080p);
+//   +-x passes: the lines are different image rows, every line needs its own pair of bulk copies, and a bulk copy costs
+//               ~20 issue slots (uniform-register set-up, lane election): 605 us against 594 us -- per-lane cp.async stays,
+//               except when a warp has a single line (D > 128), where the one pair of copies wins again (6.51 vs 6.64 ms).
 template <int K, int LPS>
 static int launch_scanline_k(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
                              cudaStream_t st) {
-    static int bulk = -1;   // development switch ADC_SO_BULK=0: ring slots filled by per-lane cp.async instead of cp.async.bulk
-    if (bulk < 0) { const char* m = getenv("ADC_SO_BULK"); bulk = m ? atoi(m) : 1; }
+    static int mode = -1;   // development switch ADC_SO_BULK: 0 = never, 2 = always, default = the rule above
+    if (mode < 0) { const char* m = getenv("ADC_SO_BULK"); mode = m ? atoi(m) : 1; }
+    const bool bulk = mode == 0 ? false : (mode == 2 ? true : (sy != 0 || LPS == 32));
     if (P.dm.D == K * LPS) return bulk ? launch_scanline_kf<K, LPS, true, true>(P, w, src, dst, sx, sy, st)
                                        : launch_scanline_kf<K, LPS, true, false>(P, w, src, dst, sx, sy, st);
     return bulk ? launch_scanline_kf<K, LPS, false, true>(P, w, src, dst, sx, sy, st)

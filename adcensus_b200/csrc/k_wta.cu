@@ -13,8 +13,8 @@ __device__ __forceinline__ float adc_subpixel(float c1, float c2, float cmin, in
 // ---------------------------------------------------------------------------------------------
 // One kernel, both views, any disparity range.  A CTA owns WT_PX neighbouring pixels of one image row -- as pixels of
 // the left view AND as pixels of the right view -- and sweeps the disparity range in chunks of WT_DC.  Per chunk two
-// small tiles are staged in shared memory (coalesced 128-bit loads, all of a thread's loads in flight before the first
-// store):
+// small tiles are staged in shared memory (coalesced 128-bit loads, issued one chunk ahead: they land in registers while
+// the previous chunk is scanned):
 //   left tile   L[t][k] = cost(x0 + t, d0 + k)                          the chunk of the CTA's own columns
 //   right tile  R[k][r] = cost(x0 + r + dmin + d0 + k, d0 + k)          cost_R(xr, d) = cost_L(xr + d, d) (:262-287),
 //                                                                       stored skewed: the diagonal a right pixel walks is a
@@ -23,7 +23,7 @@ __device__ __forceinline__ float adc_subpixel(float c1, float c2, float cmin, in
 // carrying (minimum, argmin) in registers from chunk to chunk: three instructions per cost.  A column outside the image
 // is Large_Float: never the minimum (the running minimum starts there).  The two parabola neighbours of each minimum
 // are fetched afterwards (four L2 hits per pixel), Large_Float where the reference's cost_local holds it (:277-286).
-// Shared memory per CTA is independent of the disparity range (17 KB), so the kernel keeps eight CTAs per SM at D = 64
+// Shared memory per CTA is independent of the disparity range (17 KB), so the kernel keeps six CTAs per SM at D = 64
 // as at D = 256 -- the first version staged (WT_PX + D - 1) whole columns, 172 KB for a 64-thread CTA at D = 192.
 // The right tile's columns are the left tile of the neighbouring CTAs: they come out of L2.
 // ---------------------------------------------------------------------------------------------
@@ -32,7 +32,7 @@ __device__ __forceinline__ float adc_subpixel(float c1, float c2, float cmin, in
 #define WT_LS (WT_DC + 1)      // row stride of the left tile (odd: thread t walks bank t + k)
 #define WT_RT ((WT_PX + WT_DC - 1 + WT_PX / 4 - 1) / (WT_PX / 4))   // staging trips of the right tile (32 columns per trip)
 
-__global__ void __launch_bounds__(WT_PX, 8)
+__global__ void __launch_bounds__(WT_PX, 6)
 k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, float* __restrict__ disp_r) {
     __shared__ float tl[WT_PX * WT_LS];
     __shared__ float tr[WT_DC * WT_PX];
@@ -44,12 +44,12 @@ k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, flo
     const float4 LARGE4 = make_float4(ADC_LARGE_F, ADC_LARGE_F, ADC_LARGE_F, ADC_LARGE_F);
     float lbest = ADC_LARGE_F, rbest = ADC_LARGE_F;     // min_cost starts at Large_Float (:209, :266)
     int lbd = -1, rbd = -1;                             // argmin as index d - dmin, -1 = none yet
-    for (int d0 = 0; d0 < D; d0 += WT_DC) {
-        const int dn = min(WT_DC, D - d0);
+    float4 vl[WT_PX / 32], vr[WT_RT];
+    // The loads of chunk c + 1 are issued before chunk c is scanned and land in registers while the scan runs.
+    auto fetch = [&](int d0) {
         const bool qin = d0 + 4 * kq < Dp;              // this float4 exists (Dp is a multiple of 4)
         const float* cv = rowv + d0 + 4 * kq;
         const int cb = x0 + dm.dmin + d0;               // image column of column 0 of the right tile
-        float4 vl[WT_PX / 32], vr[WT_RT];
 #pragma unroll
         for (int i = 0; i < WT_PX / 32; i++) {          // left tile: columns x0 .. x0 + WT_PX - 1
             const int x = x0 + cj + 32 * i;
@@ -60,6 +60,10 @@ k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, flo
             const int j = cj + 32 * i, x = cb + j;
             vr[i] = (qin && j < WT_PX + WT_DC - 1 && x >= 0 && x < W) ? __ldg(reinterpret_cast<const float4*>(cv + x * Dp)) : LARGE4;
         }
+    };
+    fetch(0);
+    for (int d0 = 0; d0 < D; d0 += WT_DC) {
+        const int dn = min(WT_DC, D - d0);
 #pragma unroll
         for (int i = 0; i < WT_PX / 32; i++) {
             float* o = tl + (cj + 32 * i) * WT_LS + 4 * kq;
@@ -76,6 +80,7 @@ k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, flo
             }
         }
         __syncthreads();
+        if (d0 + WT_DC < D) fetch(d0 + WT_DC);
         // ---- scans: thread t = left pixel x0 + t and right pixel x0 + t; indices relative to the chunk
         const float* pl = tl + t * WT_LS;
         const float* pr = tr + t;

@@ -422,3 +422,27 @@ def test_sharded_batch_real_engine(tmp_path, world):
     for p, (so, se) in zip(procs, outs):
         assert p.returncode == 0, se[-3000:]
     assert "SHARD_OK" in outs[0][0]
+
+
+def test_loaded_gpu_batch_equals_reference(cone):
+    """Every map of a batch that really loads the GPU (default wave size and lane count, several waves in flight, two
+    calls back to back) against the reference's sha256.  Single-pair runs leave most SMs idle and hid a shared-memory
+    proxy-ordering bug of the scanline ring that corrupted about one pair in four of a full wave."""
+    import json
+    import torch
+    left, right = cone
+    h, w, _ = left.shape
+    want = json.loads(str(np.load(T.GOLDEN_DIR / "golden_cone_full.npz")["hashes"]))["MEDIAN/DISP_L"]
+    eng = _engine(w, h, T.default_option())
+    n = 4 * eng.wave_pairs + 3
+    dl = torch.from_numpy(np.repeat(left[None], n, 0)).cuda()
+    dr = torch.from_numpy(np.repeat(right[None], n, 0)).cuda()
+    dd = torch.zeros((n, h, w), dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream()
+    for _ in range(2):
+        eng.match_batch_device(n, dl.data_ptr(), dr.data_ptr(), dd.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    out = dd.cpu().numpy()
+    bad = [i for i in range(n) if T.sha(out[i]) != want]
+    assert not bad, f"{len(bad)} of {n} maps differ from the reference: pairs {bad[:8]}"
+    eng.close()
