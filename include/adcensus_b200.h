@@ -149,7 +149,7 @@ int adc_get_config(const adc_engine* e, adc_config* out);
  * wave of wave_pairs pairs: kernel_id 0 = cost volume, 1 = horizontal arm sum, 2 = vertical arm sum
  * with division, 3 = scanline pass along x, 4 = scanline pass along y, 5 = WTA left+right, 6 / 7 = the fused
  * vertical / horizontal double pass of the aggregation (divide + sum, intermediate in shared memory), 8 = horizontal
- * arm sum with division.
+ * arm sum with division, 9 = vertical arm sum without division.
  * algorithmic_bytes (optional) receives the bytes one launch must move. */
 int adc_profile_kernel(adc_engine* e, int32_t kernel_id, int32_t reps, float* avg_ms, double* algorithmic_bytes);
 
