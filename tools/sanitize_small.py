@@ -9,7 +9,10 @@ import adcensus_b200 as A
 import adc_testlib as T
 
 cases = [(97, 61, 24, 2, {}), (130, 70, 37, 3, {}), (80, 60, 32, 10, {"do_discontinuity_adjustment": 1}),
-         (80, 60, 32, 31, {"min_disparity": 2, "max_disparity": 34})]
+         (80, 60, 32, 31, {"min_disparity": 2, "max_disparity": 34}),
+         (70, 44, 64, 4, {}),        # D = 64: eight quads per CTA (compile-time strides), 8 lanes per scanline
+         (150, 40, 130, 12, {}),     # 16 lanes per scanline, padded disparity stride
+         (600, 16, 12, 18, {})]      # a row cut into segments by the fused horizontal double pass
 for (w, h, D, seed, over) in cases:
     left, right = T.synthetic_pair(w, h, D, seed)
     kw = dict(max_disparity=D); kw.update(over)
