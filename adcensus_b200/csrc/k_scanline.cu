@@ -26,7 +26,6 @@
 // (bit d = d2(d) < tso); the bit string is a window of a per-row bit vector of the right image
 // stored mirrored, so that increasing d walks increasing bit positions.
 #include "adc_common.cuh"
-#include <stdlib.h>
 
 template <int K>
 struct Piece { static constexpr int G = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1); static constexpr int NP = K / G; };
@@ -208,7 +207,8 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
     const int pair = blockIdx.y;
     const int n_lines = sx ? dm.H : dm.W, n_steps = sx ? dm.W : dm.H;
     const bool live = line < n_lines;            // dead groups run along (uniform control flow) but move no data
-    const int W = dm.W, D = dm.D, Dp = dm.Dp;
+    // FULL: D == Dp == K * LPS is known at compile time, and with it every chunk count, slot size and stride below
+    const int W = dm.W, D = FULL ? K * LPS : dm.D, Dp = FULL ? K * LPS : dm.Dp;
     const int pstep = sx + sy * W;               // signed pixel stride along the path
     const int nrec = so_rec_words(Dp);
     const int cost_chunks = Dp >> 2, rec_chunks = nrec >> 2;      // 16-byte chunks per step
@@ -376,22 +376,18 @@ static int launch_scanline_kf(const AdcParams& P, const AdcWave& w, const float*
     return 0;
 }
 
-// Which way a pass fills its ring (measured on B200, wave of 32 Cone pairs / KITTI shape / 1080p):
-//   +-y passes: the warp's lines are adjacent columns, one bulk copy (+ one for the records) fills the whole slot -- 543 us
-//               against 571 us with per-lane cp.async (Cone), 6.30 against 6.82 ms (1080p);
-//   +-x passes: the lines are different image rows, every line needs its own pair of bulk copies, and a bulk copy costs
-//               ~20 issue slots (uniform-register set-up, lane election): 605 us against 594 us -- per-lane cp.async stays,
-//               except when a warp has a single line (D > 128), where the one pair of copies wins again (6.51 vs 6.64 ms).
+// Which way a pass fills its ring.  Measured on B200 per pass of a wave (x / y direction), cp.async vs bulk:
+//   8 lanes per line  (Cone, D = 64):        582 / 521 us  vs  592 / 537 us
+//   16 lanes per line (1242x375, D = 128):   2.67 / 2.44 ms vs 2.68 / 2.46 ms
+//   32 lanes per line (1920x1080, D = 192):  6.61 / 6.86 ms vs 6.44 / 6.32 ms
+// A bulk copy costs ~20 issue slots (uniform-register set-up, lane election) and every refill needs a proxy fence; it pays
+// when one copy moves a whole warp's step (a single line of D > 128 disparities), not when a warp steps four short lines.
 template <int K, int LPS>
 static int launch_scanline_k(const AdcParams& P, const AdcWave& w, const float* src, float* dst, int sx, int sy,
                              cudaStream_t st) {
-    static int mode = -1;   // development switch ADC_SO_BULK: 0 = never, 2 = always, default = the rule above
-    if (mode < 0) { const char* m = getenv("ADC_SO_BULK"); mode = m ? atoi(m) : 1; }
-    const bool bulk = mode == 0 ? false : (mode == 2 ? true : (sy != 0 || LPS == 32));
-    if (P.dm.D == K * LPS) return bulk ? launch_scanline_kf<K, LPS, true, true>(P, w, src, dst, sx, sy, st)
-                                       : launch_scanline_kf<K, LPS, true, false>(P, w, src, dst, sx, sy, st);
-    return bulk ? launch_scanline_kf<K, LPS, false, true>(P, w, src, dst, sx, sy, st)
-                : launch_scanline_kf<K, LPS, false, false>(P, w, src, dst, sx, sy, st);
+    constexpr bool bulk = LPS == 32;
+    if (P.dm.D == K * LPS) return launch_scanline_kf<K, LPS, true, bulk>(P, w, src, dst, sx, sy, st);
+    return launch_scanline_kf<K, LPS, false, bulk>(P, w, src, dst, sx, sy, st);
 }
 
 void adc_launch_so_bitrows(const AdcParams& P, const AdcWave& w, cudaStream_t st, unsigned long long* launches) {

@@ -29,12 +29,13 @@ __device__ __forceinline__ float adc_subpixel(float c1, float c2, float cmin, in
 // ---------------------------------------------------------------------------------------------
 #define WT_PX 128
 #define WT_DC 16
-#define WT_LS (WT_DC + 1)      // row stride of the left tile (odd: thread t walks bank t + k)
+#define WT_LS (WT_DC + 4)      // row stride of the left tile: rows stay 16-byte aligned (128-bit stores and loads), and the
+                               // eight threads of a 128-bit load phase hit eight different 16-byte bank groups (20 t mod 32)
 #define WT_RT ((WT_PX + WT_DC - 1 + WT_PX / 4 - 1) / (WT_PX / 4))   // staging trips of the right tile (32 columns per trip)
 
 __global__ void __launch_bounds__(WT_PX, 6)
 k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, float* __restrict__ disp_r) {
-    __shared__ float tl[WT_PX * WT_LS];
+    __shared__ __align__(16) float tl[WT_PX * WT_LS];
     __shared__ float tr[WT_DC * WT_PX];
     const int pair = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * WT_PX;
     const int W = dm.W, D = dm.D, Dp = dm.Dp;
@@ -66,8 +67,7 @@ k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, flo
         const int dn = min(WT_DC, D - d0);
 #pragma unroll
         for (int i = 0; i < WT_PX / 32; i++) {
-            float* o = tl + (cj + 32 * i) * WT_LS + 4 * kq;
-            o[0] = vl[i].x; o[1] = vl[i].y; o[2] = vl[i].z; o[3] = vl[i].w;
+            *reinterpret_cast<float4*>(tl + (cj + 32 * i) * WT_LS + 4 * kq) = vl[i];
         }
 #pragma unroll
         for (int i = 0; i < WT_RT; i++) {               // element k of tile column j belongs to right pixel r = j - k
@@ -87,10 +87,15 @@ k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, flo
         int lk = -1, rk = -1;
         if (dn == WT_DC) {
 #pragma unroll
-            for (int k = 0; k < WT_DC; k++) {
-                const float a = pl[k], b = pr[k * WT_PX];
-                if (lbest > a) { lbest = a; lk = k; }
-                if (rbest > b) { rbest = b; rk = k; }
+            for (int k4 = 0; k4 < WT_DC; k4 += 4) {
+                const float4 a4 = *reinterpret_cast<const float4*>(pl + k4);
+                const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float b = pr[(k4 + j) * WT_PX];
+                    if (lbest > a[j]) { lbest = a[j]; lk = k4 + j; }
+                    if (rbest > b) { rbest = b; rk = k4 + j; }
+                }
             }
         } else {
             for (int k = 0; k < dn; k++) {
