@@ -82,6 +82,8 @@ void adc_launch_gray_census(const AdcParams& P, const AdcWave& w, cudaStream_t s
 // are staged once per CTA, replicated (x32 for the 64-entry census table, x8 for the 766-entry AD
 // table) so that the data-dependent lookups of a warp spread over the banks: the first two versions
 // of this kernel were bound by L1 / shared-memory bank conflicts on exactly these gathers.
+// (Measured and rejected in round 2: lanes = 32 consecutive disparities of one pixel -- half the index arithmetic, but
+//  32-bit stores and data-dependent table addresses that differ in every lane: 631 us against 486 us per wave of 32 Cone pairs.)
 // ---------------------------------------------------------------------------------------------
 #define CV_AD_REP 8
 
