@@ -76,31 +76,50 @@ void adc_launch_gray_census(const AdcParams& P, const AdcWave& w, cudaStream_t s
 // host's libm expf, evaluated in the reference's order  ((1 - e_ad) + 1) - e_cen
 // (cost_computor.cpp:110-117), so the volume is bit-identical to the CPU path by construction.
 //
-// One CTA walks a whole image row in chunks of `ppc` pixels.  Per chunk the right-image span the
-// chunk can match is staged in shared memory as packed BGR words + census words, split into four
-// arrays by (index mod 4) so that the stride-4 walk of a thread quad is conflict-free.  The tables
-// are staged once per CTA, replicated (x32 for the 64-entry census table, x8 for the 766-entry AD
-// table) so that the data-dependent lookups of a warp spread over the banks: the first two versions
-// of this kernel were bound by L1 / shared-memory bank conflicts on exactly these gathers.
+// A thread computes a 4 x 4 block: four neighbouring pixels x0 .. x0 + 3 (x0 a multiple of 4 inside the CTA's segment of
+// the row) times four consecutive disparities 4q .. 4q + 3.  Pixel x0 + i at disparity index 4q + j is matched against
+// right-image column x0 + i - dmin - 4q - j: the sixteen pairs of the block touch only SEVEN right-image entries (they
+// are constant along the diagonals), which sit in two consecutive, 16-byte-aligned vectors of the staged row -- the row
+// is staged with an offset that makes that true for every block.  Per block: 2 x 3 128-bit loads of right-image entries
+// (packed BGR, low and high census words), 3 of left-image entries (broadcast to the lanes that share the pixels), 32
+// table look-ups, four 128-bit stores (a warp writes 2 x 4 runs of 256 contiguous bytes).
+// What bounds the kernel is shared-memory bandwidth (one wavefront per clock and SM): version 3 fetched every entry once
+// per pair (3 words per cost) and spent 3 wavefronts per AD look-up on bank conflicts -- 7 wavefronts per 32 costs; this
+// one needs 4.9.  The tables are staged once per CTA, replicated (x32 for the 64-entry census table: conflict-free;
+// x16 for the 766-entry AD table: two lanes per replica) so that the data-dependent look-ups of a warp spread over the
+// banks.
 // (Measured and rejected in round 2: lanes = 32 consecutive disparities of one pixel -- half the index arithmetic, but
-//  32-bit stores and data-dependent table addresses that differ in every lane: 631 us against 486 us per wave of 32 Cone pairs.)
+//  32-bit stores and table addresses that differ in every lane: 631 us against 486 us per wave of 32 Cone pairs; one pixel x
+//  four disparities per thread with a single 128-bit load per array out of four shifted copies of the row: half the
+//  instructions of version 3 and exactly its time, 482 us -- same shared-memory wavefronts.)
 // ---------------------------------------------------------------------------------------------
-#define CV_AD_REP 8
+#define CV_AD_REP 16
+#define CV_SEG_COLS 928       // columns per CTA at most: longer rows are cut into segments (multiple of 4)
 
-__global__ void __launch_bounds__(1024)
-k_cost_volume(AdcDims dm, int ppc, const unsigned* __restrict__ bgrx,
+__host__ __device__ inline int cv_pads(int D) { return 4 + ((4 - (D & 3)) & 3); }                  // (D + pads) % 4 == 0, pads >= 4
+__host__ __device__ inline int cv_row_len(int Lx, int D) { return (Lx + D + cv_pads(D) + 3) & ~3; }  // staged right-image entries
+
+template <bool EXACT>     // EXACT: D is a multiple of 4, no padding disparities
+__global__ void __launch_bounds__(512)
+k_cost_volume(AdcDims dm, int gpc, int nseg, int Lx, const unsigned* __restrict__ bgrx,
               const unsigned long long* __restrict__ census, float* __restrict__ vol,
               const float* __restrict__ lut_ad, const float* __restrict__ lut_cen) {
     extern __shared__ __align__(16) unsigned char cv_smem[];
-    const int pair = blockIdx.y, y = blockIdx.x;
-    const int Q = dm.Dp >> 2;                       // threads per pixel
-    const int span = dm.W + dm.D - 1;               // right-image columns -(dmax-1)-dmin .. : every xr any pixel of the row can ask for
-    const int sq = (span + 3) / 4 + 1;              // entries per residue array (padded)
-    const int xr_base = -(dm.D - 1) - dm.dmin;      // image column of staged entry 0 (xr = x - dmin - di, x = 0, di = D-1)
+    const int pair = blockIdx.y, y = blockIdx.x / nseg, seg = blockIdx.x - y * nseg;
+    const int xa = seg * Lx, xb = min(dm.W, xa + Lx);   // this CTA's columns of row y (xa is a multiple of 4)
+    const int Q = dm.Dp >> 2;                           // threads per pixel group
+    const int pads = cv_pads(dm.D);
+    const int LA = cv_row_len(Lx, dm.D);
+    const int span = xb - xa + dm.D - 1;                // right-image columns a pixel of the segment can ask for: entry e is
+    const int xr_base = xa - (dm.D - 1) - dm.dmin;      // column xr_base + e (xr = x - dmin - di; x = xa, di = D - 1 is entry 0)
     float* s_ce = reinterpret_cast<float*>(cv_smem);                                      // [64][32]
     float* s_ad = s_ce + 64 * 32;                                                         // [766][CV_AD_REP]
-    unsigned long long* s_cen = reinterpret_cast<unsigned long long*>(s_ad + 766 * CV_AD_REP);  // [4][sq]
-    unsigned* s_bgr = reinterpret_cast<unsigned*>(s_cen + 4 * sq);                        // [4][sq]
+    unsigned* s_rb = reinterpret_cast<unsigned*>(s_ad + 766 * CV_AD_REP);                 // [LA] right image: entry e at position e + pads
+    unsigned* s_rl = s_rb + LA;                                                           //      census bits 0..31
+    unsigned* s_rh = s_rl + LA;                                                           //      census bits 32..63
+    unsigned* s_lb = s_rh + LA;                                                           // [Lx] left image, column xa + i at position i
+    unsigned* s_ll = s_lb + Lx;
+    unsigned* s_lh = s_ll + Lx;
     const unsigned* left = bgrx + (size_t)pair * 2 * dm.N;
     const unsigned* right = left + (size_t)dm.N;
     const unsigned long long* cen_l = census + (size_t)pair * 2 * dm.N;
@@ -109,60 +128,82 @@ k_cost_volume(AdcDims dm, int ppc, const unsigned* __restrict__ bgrx,
     const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) s_ce[i] = __ldg(lut_cen + (i >> 5));
     for (int i = threadIdx.x; i < 766 * CV_AD_REP; i += blockDim.x) s_ad[i] = __ldg(lut_ad + i / CV_AD_REP);
-    // the whole right-image row, once: packed BGR + census, split by (index mod 4)
-    for (int i = threadIdx.x; i < span; i += blockDim.x) {
-        const int xr = xr_base + i;
+    for (int i = threadIdx.x; i < LA; i += blockDim.x) {
+        const int e = i - pads, xr = xr_base + e;
         unsigned long long c = 0ull;
         unsigned pix = 0xffffffffu;                 // marker: outside the image
-        if (xr >= 0 && xr < dm.W) {
+        if (e >= 0 && e < span && xr >= 0 && xr < dm.W) {
             c = __ldg(cen_r + row + xr);
             pix = __ldg(right + row + xr);
         }
-        s_cen[(i & 3) * sq + (i >> 2)] = c;
-        s_bgr[(i & 3) * sq + (i >> 2)] = pix;
+        s_rb[i] = pix; s_rl[i] = (unsigned)c; s_rh[i] = (unsigned)(c >> 32);
+    }
+    for (int i = threadIdx.x; i < Lx; i += blockDim.x) {
+        unsigned long long c = 0ull;
+        unsigned pix = 0u;
+        if (xa + i < xb) { c = __ldg(cen_l + row + xa + i); pix = __ldg(left + row + xa + i); }
+        s_lb[i] = pix; s_ll[i] = (unsigned)c; s_lh[i] = (unsigned)(c >> 32);
     }
     __syncthreads();
-    const int p = threadIdx.x / Q, q = threadIdx.x - p * Q;
-    if (p >= ppc) return;
-    for (int x = p; x < dm.W; x += ppc) {
-        const unsigned cl = __ldg(left + row + x);
-        const unsigned long long bl = __ldg(cen_l + row + x);
-        float out[4];
-        const int i0 = (x - dm.dmin - 4 * q) - xr_base;   // staged index of xr = x - dmin - di for di = 4q; in [0, W+D-2] for real disparities
+    const int g0 = threadIdx.x / Q, q = threadIdx.x - g0 * Q;
+    if (g0 >= gpc) return;
+    const float* t_ad = s_ad + (lane & (CV_AD_REP - 1));
+    const float* t_ce = s_ce + lane;
+    const int ngroups = (xb - xa + 3) >> 2;
+    float* vrow = vol + (size_t)pair * dm.vol_stride + ((size_t)row + xa) * dm.Dp;
+    for (int g = g0; g < ngroups; g += gpc) {
+        // block (i, j): entry e0 + 3 - j + i with e0 = 4g + D - 4 - 4q >= -3; position e0 + pads is a multiple of 4
+        const int p0 = 4 * g + dm.D - 4 - 4 * q + pads;
+        const uint4 b0 = *reinterpret_cast<const uint4*>(s_rb + p0), b1 = *reinterpret_cast<const uint4*>(s_rb + p0 + 4);
+        const uint4 l0 = *reinterpret_cast<const uint4*>(s_rl + p0), l1 = *reinterpret_cast<const uint4*>(s_rl + p0 + 4);
+        const uint4 h0 = *reinterpret_cast<const uint4*>(s_rh + p0), h1 = *reinterpret_cast<const uint4*>(s_rh + p0 + 4);
+        const uint4 cb = *reinterpret_cast<const uint4*>(s_lb + 4 * g), cl = *reinterpret_cast<const uint4*>(s_ll + 4 * g),
+                    ch = *reinterpret_cast<const uint4*>(s_lh + 4 * g);
+        const unsigned rb[7] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z};
+        const unsigned rl[7] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z};
+        const unsigned rh[7] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z};
+        const unsigned lb[4] = {cb.x, cb.y, cb.z, cb.w}, ll[4] = {cl.x, cl.y, cl.z, cl.w}, lh[4] = {ch.x, ch.y, ch.z, ch.w};
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            // branch-free: padding lanes (di >= D) and out-of-image matches compute on clamped operands and are
-            // overwritten by selects -- the per-disparity branches used to cost more than the arithmetic
-            const int di = 4 * q + j;
-            const int i = max(i0 - j, 0);
-            const int si = (i & 3) * sq + (i >> 2);
-            const unsigned pix = s_bgr[si];
-            const int sad = min((int)__vsadu4(cl, pix), 765);           // |dB| + |dG| + |dR| (4th byte is 0 in both)
-            const int ham = __popcll(bl ^ s_cen[si]) & 63;
-            float c = __fsub_rn(s_ad[sad * CV_AD_REP + (lane & (CV_AD_REP - 1))], s_ce[ham * 32 + lane]);
-            c = pix == 0xffffffffu ? 1.0f : c;                          // out-of-image match: cost_computor.cpp:101-104
-            out[j] = di < dm.D ? c : 0.0f;                              // padding lane, never read as a cost
+        for (int i = 0; i < 4; i++) {
+            float out[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                // branch-free: padding disparities (di >= D) and out-of-image matches compute on whatever the entry holds and
+                // are overwritten by selects -- the per-disparity branches used to cost more than the arithmetic
+                const int c = 3 - j + i;
+                const int sad = min((int)__vsadu4(lb[i], rb[c]), 765);     // |dB| + |dG| + |dR| (4th byte is 0 in both; the marker clamps)
+                const int ham = (__popc(ll[i] ^ rl[c]) + __popc(lh[i] ^ rh[c])) & 63;
+                float v = __fsub_rn(t_ad[sad * CV_AD_REP], t_ce[ham * 32]);
+                v = rb[c] == 0xffffffffu ? 1.0f : v;                        // out-of-image match: cost_computor.cpp:101-104
+                out[j] = (EXACT || 4 * q + j < dm.D) ? v : 0.0f;            // padding disparity, never read as a cost
+            }
+            if (xa + 4 * g + i < xb)
+                *reinterpret_cast<float4*>(vrow + (size_t)(4 * g + i) * dm.Dp + 4 * q) = make_float4(out[0], out[1], out[2], out[3]);
         }
-        float4* dst = reinterpret_cast<float4*>(vol + (size_t)pair * dm.vol_stride + ((size_t)row + x) * dm.Dp) + q;
-        *dst = make_float4(out[0], out[1], out[2], out[3]);
     }
 }
 
 void adc_launch_cost(const AdcParams& P, const AdcWave& w, float* vol, cudaStream_t st, unsigned long long* launches) {
     const int Q = P.dm.Dp / 4;
-    int ppc = 512 / Q;                              // pixels in flight per CTA
-    if (ppc > 32) ppc = 32;
-    if (ppc < 1) ppc = 1;
-    const int threads = ppc * Q;
-    const int span = P.dm.W + P.dm.D - 1, sq = (span + 3) / 4 + 1;
-    const size_t smem = (size_t)(64 * 32 + 766 * CV_AD_REP) * 4 + (size_t)4 * sq * 12;
+    const int nseg = (P.dm.W + CV_SEG_COLS - 1) / CV_SEG_COLS;
+    const int Lx = (((P.dm.W + nseg - 1) / nseg) + 3) & ~3;                // columns per segment, a multiple of 4
+    const int groups = Lx / 4;
+    int gmax = 512 / Q;                             // pixel groups in flight per CTA
+    if (gmax > 32) gmax = 32;
+    if (gmax < 1) gmax = 1;
+    const int trips = (groups + gmax - 1) / gmax;
+    const int gpc = (groups + trips - 1) / trips;   // ... evened out over the trips
+    const int threads = (gpc * Q + 31) / 32 * 32;
+    const size_t smem = (size_t)(64 * 32 + 766 * CV_AD_REP) * 4 + (size_t)3 * cv_row_len(Lx, P.dm.D) * 4 + (size_t)3 * Lx * 4;
     static AdcOnce attr_once;
     if (adc_once_needed(attr_once)) {
-        cudaFuncSetAttribute(k_cost_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_cost_volume<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(k_cost_volume<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         adc_once_done(attr_once);
     }
-    dim3 grid(P.dm.H, w.S);
-    k_cost_volume<<<grid, threads, smem, st>>>(P.dm, ppc, w.bgrx, w.census, vol, w.lut_ad, w.lut_cen);
+    dim3 grid(P.dm.H * nseg, w.S);
+    if (P.dm.D == P.dm.Dp) k_cost_volume<true><<<grid, threads, smem, st>>>(P.dm, gpc, nseg, Lx, w.bgrx, w.census, vol, w.lut_ad, w.lut_cen);
+    else k_cost_volume<false><<<grid, threads, smem, st>>>(P.dm, gpc, nseg, Lx, w.bgrx, w.census, vol, w.lut_ad, w.lut_cen);
     ++*launches;
 }
 

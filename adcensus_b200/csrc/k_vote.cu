@@ -145,12 +145,14 @@ __device__ __forceinline__ void vote_scan_region(int p, int W, const uchar4* __r
 }
 
 // ---- batch-wide scan: histogram of every slot (D counters packed two per 32-bit word; a region holds < 65536 pixels) and,
-// when there is room, its forward list: the pending pixels (slots) of its region, written compacted at a base taken from
-// the pair's cursor (counters[9]).
+// when there is room, its forward list: an entry (t, s) for every pending pixel t of the region of slot s, written compacted
+// at a base taken from the pair's cursor (counters[9]).  A slot reserves as many entries as its region has pixels and marks
+// the ones it does not use (-1): the lists of a pair are ONE dense array of `room` entries that k_vote_push streams through.
+__host__ __device__ inline long long vote_fwd_offset(long long ns, int HW) { return (ns * HW + 1) & ~1ll; }   // in 32-bit words, 8-byte aligned
 __global__ void __launch_bounds__(VI_WARPS * 32)
 k_vote_scan(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restrict__ alr_all, const int* __restrict__ vstate_all,
             const uint16_t* __restrict__ sup_all, const int* __restrict__ vlist, int* counters, unsigned* __restrict__ hist_all,
-            long long hist_stride, int* __restrict__ scratch_all, int force_enum) {
+            long long hist_stride, int force_enum) {
     __shared__ int s_hist[VI_WARPS][VP_MAXD];
     const AdcDims& dm = P.dm;
     const int pair = blockIdx.y;
@@ -159,22 +161,21 @@ k_vote_scan(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restri
     int* cnt = counters + pair * ADC_CNT;
     const int n0 = cnt[10], n1 = cnt[11], ns = n0 + n1;
     const long long room = (unsigned)cnt[15];
-    const bool use_fwd = !force_enum && (long long)ns * HW + room <= hist_stride;
+    const bool use_fwd = !force_enum && vote_fwd_offset(ns, HW) + 2 * room <= hist_stride;
     const uchar4* A = arms + (size_t)pair * dm.N;
     const uchar2* ALR = alr_all + (size_t)pair * dm.N;
     const int* VS = vstate_all + (size_t)pair * dm.N;
     const uint16_t* sup = sup_all + (size_t)pair * dm.N;
     unsigned* hist = hist_all + (size_t)pair * hist_stride;
-    int* fwd = reinterpret_cast<int*>(hist + (size_t)ns * HW);
-    int* fbase = scratch_all + (size_t)pair * 2 * dm.N;
-    int* fcnt = fbase + dm.N;
+    int2* fwd = reinterpret_cast<int2*>(hist + vote_fwd_offset(ns, HW));
     int* hs = s_hist[wid];
     for (int s = blockIdx.x * VI_WARPS + wid; s < ns; s += gridDim.x * VI_WARPS) {
         const int p = s < n0 ? vlist[((size_t)pair * 2 + 0) * dm.N + s] : vlist[((size_t)pair * 2 + 1) * dm.N + (s - n0)];
         for (int b = lane; b < D; b += 32) hs[b] = 0;
         int fb = 0, fn = 0;
+        const int reserved = (int)sup[p];
         if (use_fwd) {
-            if (lane == 0) fb = atomicAdd(cnt + 9, (int)sup[p]);
+            if (lane == 0) fb = atomicAdd(cnt + 9, reserved);
             fb = __shfl_sync(0xffffffffu, fb, 0);
         }
         __syncwarp();
@@ -183,7 +184,7 @@ k_vote_scan(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restri
             if (use_fwd) {
                 const bool edge = v < -1 && -v - 2 != s;
                 const unsigned m = __ballot_sync(0xffffffffu, edge);
-                if (edge) fwd[fb + fn + __popc(m & ((1u << lane) - 1u))] = -v - 2;
+                if (edge) fwd[fb + fn + __popc(m & ((1u << lane) - 1u))] = make_int2(-v - 2, s);
                 fn += __popc(m);
             }
         });
@@ -192,7 +193,8 @@ k_vote_scan(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restri
             const unsigned c0 = (unsigned)hs[2 * w2], c1 = (2 * w2 + 1 < D) ? (unsigned)hs[2 * w2 + 1] : 0u;
             hist[(size_t)s * HW + w2] = c0 | (c1 << 16);
         }
-        if (use_fwd && lane == 0) { fbase[s] = fb; fcnt[s] = fn; }
+        if (use_fwd)
+            for (int k2 = fn + lane; k2 < reserved; k2 += 32) fwd[fb + k2] = make_int2(-1, -1);
         __syncwarp();
     }
 }
@@ -207,7 +209,7 @@ k_vote_scan(AdcParams P, const uchar4* __restrict__ arms, const uchar2* __restri
 
 __global__ void __launch_bounds__(VP_THREADS)
 k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
-            const uchar2* __restrict__ atbT_all, const int* __restrict__ pslotT_all, const int* scratch_all, unsigned* hist_all, long long hist_stride, int* cur_all, uint8_t* val_all, uint8_t* flag_all,
+            const uchar2* __restrict__ atbT_all, const int* __restrict__ pslotT_all, unsigned* hist_all, long long hist_stride, int* cur_all, uint8_t* val_all, uint8_t* flag_all,
             const int* __restrict__ vlist, int* counters, int* work_all, int2* chg_all,
             float* disp_old, float* disp_new, uint8_t* label, int cols_cap, int slot_cap, int force_enum) {
     extern __shared__ __align__(16) unsigned char vp_smem[];
@@ -220,8 +222,6 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
     const uchar2* ALR = alr_all + (size_t)pair * dm.N;
     const uchar2* ATB = atbT_all + (size_t)pair * dm.N;
     const int* pslotT = pslotT_all + (size_t)pair * dm.N;
-    const int* fbase = scratch_all + (size_t)pair * 2 * dm.N;   // [slot] start / length of a slot's forward list
-    const int* fcnt = fbase + dm.N;
     unsigned* hist = hist_all + (size_t)pair * hist_stride;
     int* work = work_all + (size_t)pair * dm.N;
     int2* chg = chg_all + (size_t)pair * dm.N;
@@ -256,35 +256,28 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
 
     // ---- adjacency lists (CSR by target) from the forward lists of k_vote_scan: count, prefix, fill
     const long long room = (unsigned)__ldcg(cnt + 15);
-    const bool use_fwd = !force_enum && (long long)ns * HW + room <= hist_stride;
-    const int* fwd = reinterpret_cast<const int*>(hist + (size_t)ns * HW);
-    // adjacency entry = (slot, pixel of that slot): a push needs both, and one 8-byte load is one L2 round trip less
-    int2* adj = reinterpret_cast<int2*>(reinterpret_cast<int*>(hist) + ((((long long)ns * HW + (use_fwd ? room : 0)) + 1) & ~1ll));   // 8-byte aligned
+    const long long fwd_off = vote_fwd_offset(ns, HW);
+    const bool use_fwd = !force_enum && fwd_off + 2 * room <= hist_stride;
+    const int2* fwd = reinterpret_cast<const int2*>(hist + fwd_off);
+    // adjacency entry = the slot whose histogram counts the target.  (Whether that slot's pixel comes after the target in
+    // raster order -- all a push needs to know about it -- is a comparison of slot numbers: the lists are in raster order.)
+    int* adj = reinterpret_cast<int*>(hist) + fwd_off + (use_fwd ? 2 * room : 0);
     unsigned long long t_start = 0;
     if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
-    // Both passes over the forward lists: a warp takes 32 consecutive slots at a time (their list descriptors in one
-    // coalesced load, handed out by shuffle), two lists per trip, two entries per list and lane in flight.
+    // Both passes stream through the pair's forward entries, eight independent 8-byte loads per thread in flight (the
+    // first version walked list by list, two entries per lane in flight, and spent 1.9 of the kernel's 3.6 ms here).
     auto for_each_edge = [&](auto&& f) {
-        for (int base = wid * 32; base < ns; base += VP_WARPS * 32) {
-            const int sl = base + lane;
-            const int my_fb = sl < ns ? fbase[sl] : 0, my_fn = sl < ns ? fcnt[sl] : 0, my_p = sl < ns ? pix(sl) : 0;
-            for (int j = 0; j < 32; j += 2) {
-                const int fbA = __shfl_sync(0xffffffffu, my_fb, j), fnA = __shfl_sync(0xffffffffu, my_fn, j);
-                const int fbB = __shfl_sync(0xffffffffu, my_fb, j + 1), fnB = __shfl_sync(0xffffffffu, my_fn, j + 1);
-                const int pA = __shfl_sync(0xffffffffu, my_p, j), pB = __shfl_sync(0xffffffffu, my_p, j + 1);
-                const int nmax = max(fnA, fnB);
-                for (int k = lane; k < nmax; k += 64) {
-                    const int a0 = k < fnA ? __ldg(fwd + fbA + k) : -1, a1 = k + 32 < fnA ? __ldg(fwd + fbA + k + 32) : -1;
-                    const int b0 = k < fnB ? __ldg(fwd + fbB + k) : -1, b1 = k + 32 < fnB ? __ldg(fwd + fbB + k + 32) : -1;
-                    if (a0 >= 0) f(a0, base + j, pA);
-                    if (a1 >= 0) f(a1, base + j, pA);
-                    if (b0 >= 0) f(b0, base + j + 1, pB);
-                    if (b1 >= 0) f(b1, base + j + 1, pB);
-                }
-            }
+        const int n = (int)room;                       // (< 2^30: use_fwd)
+        for (int i0 = tid; i0 < n; i0 += 8 * VP_THREADS) {
+            int2 e[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) e[j] = i0 + j * VP_THREADS < n ? __ldg(fwd + i0 + j * VP_THREADS) : make_int2(-1, -1);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (e[j].x >= 0) f(e[j].x, e[j].y);
         }
     };
-    if (use_fwd) for_each_edge([&](int t, int, int) { atomicAdd(&cur[t + 1], 1); });   // length of t's list, kept at index t + 1
+    if (use_fwd) for_each_edge([&](int t, int) { atomicAdd(&cur[t + 1], 1); });   // length of t's list, kept at index t + 1
     __syncthreads();
     // ---- inclusive prefix sum over cur[0..ns]: cur[t] = start of t's list, cur[ns] = number of entries
     if (tid == 0) { s_base = 0; s_fits = 1; }
@@ -316,9 +309,9 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
         __syncthreads();
     }
     const int n_adj = s_base;
-    const bool use_adj = use_fwd && s_fits && (long long)ns * HW + room + 1 + 2ll * n_adj <= hist_stride;
+    const bool use_adj = use_fwd && s_fits && fwd_off + 2 * room + n_adj <= hist_stride;
     // ---- fill (afterwards cur[t] = end of t's list = start of t + 1's)
-    if (use_adj) for_each_edge([&](int t, int s, int p) { adj[atomicAdd(&cur[t], 1)] = make_int2(s, p); });
+    if (use_adj) for_each_edge([&](int t, int s) { adj[atomicAdd(&cur[t], 1)] = s; });
     __syncthreads();
     if (tid == 0) {
         unsigned long long t1;
@@ -345,16 +338,16 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
         //  value into its own byte and a reader that still sees 0 merely stores it again; the flags are consumed after a barrier)
         if (!(f & VP_FLAG_DIRTY)) flg[s] = (uint8_t)VP_FLAG_DIRTY;
     };
-    auto push_adj = [&](int t, int q, int a, int b, int k, int phase) {
+    auto push_adj = [&](int t, int a, int b, int k, int phase) {
         // (global-memory cursors were advanced by L2 atomics: read them at L2)
         const int e0 = t > 0 ? (state_smem ? cur[t - 1] : __ldcg(cur + t - 1)) : 0, e1 = state_smem ? cur[t] : __ldcg(cur + t);
         for (int e = e0 + lane; e < e1; e += 128) {          // four entries per lane per trip, loads first
-            int2 v[4];
+            int v[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) v[j] = e + 32 * j < e1 ? adj[e + 32 * j] : make_int2(-1, 0);
+            for (int j = 0; j < 4; j++) v[j] = e + 32 * j < e1 ? adj[e + 32 * j] : -1;
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                if (v[j].x >= 0) touch(v[j].x, v[j].y > q, a, b, k, phase);
+                if (v[j] >= 0) touch(v[j], v[j] > t, a, b, k, phase);
         }
     };
     // Fallback: inverse region by enumeration.  p' = (px,py) has q = (qx,qy) in R(p') iff the horizontal arm of
@@ -430,6 +423,23 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
         return 255;
     };
     const int nhw = (HW + 31) / 32;   // histogram words per lane (<= 4 for D <= 254)
+    // phase clock of thread 0 (diagnostics, adc_debug_counters): ns spent collecting / deriving / pushing
+    // (kept in shared memory: only thread 0 touches them, and registers are short here)
+    __shared__ unsigned long long s_clk[4];   // mark, collect, derive, push
+    enum { ns_collect = 1, ns_derive = 2, ns_push = 3 };
+    auto lap = [&](int acc) {
+        if (tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            s_clk[acc] += t - s_clk[0];
+            s_clk[0] = t;
+        }
+    };
+    if (tid == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        s_clk[0] = t; s_clk[1] = s_clk[2] = s_clk[3] = 0;
+    }
 
     for (int it = 0; it < 5; it++) {
         for (int k = 0; k < 2; k++) {
@@ -452,38 +462,42 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
                     if (d) work[o + __popc(m & ((1u << lane) - 1u))] = base + i;
                 }
                 __syncthreads();
+                lap(ns_collect);
                 const int nwork = s_nwork;
                 if (nwork == 0) break;
                 rounds_total++;
-                // ---- derive: vote of every such pixel from its histogram, two pixels per trip
-                for (int t = 2 * wid; t < nwork; t += 2 * VP_WARPS) {
-                    const bool two = t + 1 < nwork;
-                    const int sA = work[t], sB = two ? work[t + 1] : sA;
-                    unsigned hA[4], hB[4];
+                // ---- derive: vote of every such pixel from its histogram, four pixels per trip (their loads in flight together)
+                for (int t = 4 * wid; t < nwork; t += 4 * VP_WARPS) {
+                    int sl[4];
+                    unsigned hv[4][4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int w2 = lane + 32 * j;
-                        hA[j] = (j < nhw && w2 < HW) ? __ldcg(hist + (size_t)sA * HW + w2) : 0u;
-                        hB[j] = (j < nhw && w2 < HW) ? __ldcg(hist + (size_t)sB * HW + w2) : 0u;
-                    }
-                    const int rA = vote(hA, nhw), rB = vote(hB, nhw);
-                    if (lane == 0) {
-                        derives += two ? 2 : 1;
-                        const int aA = val[sA];
-                        if (rA != aA) {
-                            val[sA] = (uint8_t)rA;
-                            chg[atomicAdd(&s_nchg, 1)] = make_int2(sA, aA | (rA << 8));
+                    for (int u = 0; u < 4; u++) sl[u] = work[min(t + u, nwork - 1)];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int w2 = lane + 32 * j;
+                            hv[u][j] = (j < nhw && w2 < HW) ? __ldcg(hist + (size_t)sl[u] * HW + w2) : 0u;
                         }
-                        if (two) {
-                            const int aB = val[sB];
-                            if (rB != aB) {
-                                val[sB] = (uint8_t)rB;
-                                chg[atomicAdd(&s_nchg, 1)] = make_int2(sB, aB | (rB << 8));
+                    }
+                    int r[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) r[u] = vote(hv[u], nhw);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (t + u >= nwork) break;
+                            derives++;
+                            const int a = val[sl[u]];
+                            if (r[u] != a) {
+                                val[sl[u]] = (uint8_t)r[u];
+                                chg[atomicAdd(&s_nchg, 1)] = make_int2(sl[u], a | (r[u] << 8));
                             }
                         }
                     }
                 }
                 __syncthreads();
+                lap(ns_derive);
                 const int nchg = s_nchg;
                 if (nchg == 0) break;
                 any_change = true;
@@ -491,11 +505,11 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
                 // ---- push the changes into the histograms of the later pixels of this list
                 for (int t = wid; t < nchg; t += VP_WARPS) {
                     const int2 c = chg[t];
-                    const int q = pix(c.x);
-                    if (use_adj) push_adj(c.x, q, c.y & 255, (c.y >> 8) & 255, k, 0);
-                    else         push_enum(q, c.y & 255, (c.y >> 8) & 255, k, 0);
+                    if (use_adj) push_adj(c.x, c.y & 255, (c.y >> 8) & 255, k, 0);
+                    else         push_enum(pix(c.x), c.y & 255, (c.y >> 8) & 255, k, 0);
                 }
                 __syncthreads();
+                lap(ns_push);
             }
             if (!any_change) continue;   // nothing moved in this sweep (uniform across the CTA)
             // ---- commit: the pixels filled by this sweep become visible to everybody and leave the list
@@ -525,7 +539,7 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
             changes += ncommit;
             for (int t = wid; t < ncommit; t += VP_WARPS) {
                 const int2 c = chg[t];
-                if (use_adj) push_adj(c.x, c.y, 255, (int)val[c.x], k, 1);
+                if (use_adj) push_adj(c.x, 255, (int)val[c.x], k, 1);
                 else         push_enum(c.y, 255, (int)val[c.x], k, 1);
             }
             __syncthreads();
@@ -535,7 +549,13 @@ k_vote_push(AdcParams P, const uchar2* __restrict__ alr_all,
     }
     derives = __reduce_add_sync(0xffffffffu, lane == 0 ? derives : 0);
     if (lane == 0) atomicAdd(cnt + 3, derives);
-    if (tid == 0) { __stcg(cnt + 2, rounds_total); __stcg(cnt + 12, changes); }
+    if (tid == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        __stcg(cnt + 2, rounds_total); __stcg(cnt + 12, changes);
+        __stcg(cnt + 5, (int)((t1 - t_start) / 1000)); __stcg(cnt + 6, (int)(s_clk[ns_derive] / 1000));      // us: whole kernel, derive phases,
+        __stcg(cnt + 7, (int)(s_clk[ns_push] / 1000)); __stcg(cnt + 8, (int)(s_clk[ns_collect] / 1000));             // push phases, collect phases
+    }
 }
 
 // Expects the active lists (w.vlist, counters 10/11), w.vote_alr and w.vote_state (valid / invalid part, from
@@ -556,8 +576,7 @@ bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st,
     if (gx < 1) gx = 1;
     dim3 igrid(gx, w.S);
     k_vote_scan<<<igrid, VI_WARPS * 32, 0, st>>>(P, w.arms, w.vote_alr, w.vote_state, w.sup_h, w.vlist, w.counters, hist,
-                                                 dm.vol_stride, w.pend /* idle until the lists are rebuilt after voting */,
-                                                 force_enum);
+                                                 dm.vol_stride, force_enum);
     const int cols_cap = (2 * L1 + 1 + 7) / 8 * 8;
     // shared memory: column lists (fallback), then val / flg / cur for as many slots as fit
     const size_t fixed = (size_t)VP_WARPS * cols_cap * 2;
@@ -570,7 +589,7 @@ bool adc_launch_vote_push(const AdcParams& P, const AdcWave& w, cudaStream_t st,
         cudaFuncSetAttribute(k_vote_push, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);   // (+ static < 227 KB)
         adc_once_done(attr_once);
     }
-    k_vote_push<<<w.S, VP_THREADS, smem, st>>>(P, w.vote_alr, w.vote_atbT, w.vote_pslotT, w.pend, hist, dm.vol_stride,
+    k_vote_push<<<w.S, VP_THREADS, smem, st>>>(P, w.vote_alr, w.vote_atbT, w.vote_pslotT, hist, dm.vol_stride,
                                               w.vote_off, w.vote_val, w.vote_dirtyb, w.vlist, w.counters, w.last_eval,
                                               w.vote_dirty, w.disp_l, w.disp_t, w.label, cols_cap, slot_cap, force_enum);
     *launches += 4;
