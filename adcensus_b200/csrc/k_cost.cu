@@ -85,7 +85,7 @@ void adc_launch_gray_census(const AdcParams& P, const AdcWave& w, cudaStream_t s
 // table look-ups, four 128-bit stores (a warp writes 2 x 4 runs of 256 contiguous bytes).
 // What bounds the kernel is shared-memory bandwidth (one wavefront per clock and SM): version 3 fetched every entry once
 // per pair (3 words per cost) and spent 3 wavefronts per AD look-up on bank conflicts -- 7 wavefronts per 32 costs; this
-// one needs 4.9.  The tables are staged once per CTA, replicated (x32 for the 64-entry census table: conflict-free;
+// one needs 4.9.  A CTA computes four consecutive rows of its segment; the tables are staged once per CTA, replicated (x32 for the 64-entry census table: conflict-free;
 // x16 for the 766-entry AD table: two lanes per replica) so that the data-dependent look-ups of a warp spread over the
 // banks.
 // (Measured and rejected in round 2: lanes = 32 consecutive disparities of one pixel -- half the index arithmetic, but
@@ -101,11 +101,11 @@ __host__ __device__ inline int cv_row_len(int Lx, int D) { return (Lx + D + cv_p
 
 template <bool EXACT>     // EXACT: D is a multiple of 4, no padding disparities
 __global__ void __launch_bounds__(512)
-k_cost_volume(AdcDims dm, int gpc, int nseg, int Lx, const unsigned* __restrict__ bgrx,
+k_cost_volume(AdcDims dm, int gpc, int nseg, int Lx, int rpc, const unsigned* __restrict__ bgrx,
               const unsigned long long* __restrict__ census, float* __restrict__ vol,
               const float* __restrict__ lut_ad, const float* __restrict__ lut_cen) {
     extern __shared__ __align__(16) unsigned char cv_smem[];
-    const int pair = blockIdx.y, y = blockIdx.x / nseg, seg = blockIdx.x - y * nseg;
+    const int pair = blockIdx.y, yb = blockIdx.x / nseg, seg = blockIdx.x - yb * nseg;   // rows yb * rpc .. of segment seg
     const int xa = seg * Lx, xb = min(dm.W, xa + Lx);   // this CTA's columns of row y (xa is a multiple of 4)
     const int Q = dm.Dp >> 2;                           // threads per pixel group
     const int pads = cv_pads(dm.D);
@@ -124,61 +124,69 @@ k_cost_volume(AdcDims dm, int gpc, int nseg, int Lx, const unsigned* __restrict_
     const unsigned* right = left + (size_t)dm.N;
     const unsigned long long* cen_l = census + (size_t)pair * 2 * dm.N;
     const unsigned long long* cen_r = cen_l + dm.N;
-    const int row = y * dm.W;
     const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) s_ce[i] = __ldg(lut_cen + (i >> 5));
-    for (int i = threadIdx.x; i < 766 * CV_AD_REP; i += blockDim.x) s_ad[i] = __ldg(lut_ad + i / CV_AD_REP);
-    for (int i = threadIdx.x; i < LA; i += blockDim.x) {
-        const int e = i - pads, xr = xr_base + e;
-        unsigned long long c = 0ull;
-        unsigned pix = 0xffffffffu;                 // marker: outside the image
-        if (e >= 0 && e < span && xr >= 0 && xr < dm.W) {
-            c = __ldg(cen_r + row + xr);
-            pix = __ldg(right + row + xr);
-        }
-        s_rb[i] = pix; s_rl[i] = (unsigned)c; s_rh[i] = (unsigned)(c >> 32);
+    for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {              // the tables, once per CTA (128-bit stores)
+        const float v = __ldg(lut_cen + (i >> 3));
+        reinterpret_cast<float4*>(s_ce)[i] = make_float4(v, v, v, v);
     }
-    for (int i = threadIdx.x; i < Lx; i += blockDim.x) {
-        unsigned long long c = 0ull;
-        unsigned pix = 0u;
-        if (xa + i < xb) { c = __ldg(cen_l + row + xa + i); pix = __ldg(left + row + xa + i); }
-        s_lb[i] = pix; s_ll[i] = (unsigned)c; s_lh[i] = (unsigned)(c >> 32);
+    for (int i = threadIdx.x; i < 766 * (CV_AD_REP / 4); i += blockDim.x) {
+        const float v = __ldg(lut_ad + i / (CV_AD_REP / 4));
+        reinterpret_cast<float4*>(s_ad)[i] = make_float4(v, v, v, v);
     }
-    __syncthreads();
     const int g0 = threadIdx.x / Q, q = threadIdx.x - g0 * Q;
-    if (g0 >= gpc) return;
     const float* t_ad = s_ad + (lane & (CV_AD_REP - 1));
     const float* t_ce = s_ce + lane;
     const int ngroups = (xb - xa + 3) >> 2;
-    float* vrow = vol + (size_t)pair * dm.vol_stride + ((size_t)row + xa) * dm.Dp;
-    for (int g = g0; g < ngroups; g += gpc) {
-        // block (i, j): entry e0 + 3 - j + i with e0 = 4g + D - 4 - 4q >= -3; position e0 + pads is a multiple of 4
-        const int p0 = 4 * g + dm.D - 4 - 4 * q + pads;
-        const uint4 b0 = *reinterpret_cast<const uint4*>(s_rb + p0), b1 = *reinterpret_cast<const uint4*>(s_rb + p0 + 4);
-        const uint4 l0 = *reinterpret_cast<const uint4*>(s_rl + p0), l1 = *reinterpret_cast<const uint4*>(s_rl + p0 + 4);
-        const uint4 h0 = *reinterpret_cast<const uint4*>(s_rh + p0), h1 = *reinterpret_cast<const uint4*>(s_rh + p0 + 4);
-        const uint4 cb = *reinterpret_cast<const uint4*>(s_lb + 4 * g), cl = *reinterpret_cast<const uint4*>(s_ll + 4 * g),
-                    ch = *reinterpret_cast<const uint4*>(s_lh + 4 * g);
-        const unsigned rb[7] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z};
-        const unsigned rl[7] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z};
-        const unsigned rh[7] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z};
-        const unsigned lb[4] = {cb.x, cb.y, cb.z, cb.w}, ll[4] = {cl.x, cl.y, cl.z, cl.w}, lh[4] = {ch.x, ch.y, ch.z, ch.w};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            float out[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                // branch-free: padding disparities (di >= D) and out-of-image matches compute on whatever the entry holds and
-                // are overwritten by selects -- the per-disparity branches used to cost more than the arithmetic
-                const int c = 3 - j + i;
-                const int sad = min((int)__vsadu4(lb[i], rb[c]), 765);     // |dB| + |dG| + |dR| (4th byte is 0 in both; the marker clamps)
-                const int ham = (__popc(ll[i] ^ rl[c]) + __popc(lh[i] ^ rh[c])) & 63;
-                float v = __fsub_rn(t_ad[sad * CV_AD_REP], t_ce[ham * 32]);
-                v = rb[c] == 0xffffffffu ? 1.0f : v;                        // out-of-image match: cost_computor.cpp:101-104
-                out[j] = (EXACT || 4 * q + j < dm.D) ? v : 0.0f;            // padding disparity, never read as a cost
+    for (int y = yb * rpc; y < min(dm.H, (yb + 1) * rpc); y++) {
+        const int row = y * dm.W;
+        if (y > yb * rpc) __syncthreads();                // everybody is done with the previous row's entries
+        for (int i = threadIdx.x; i < LA; i += blockDim.x) {
+            const int e = i - pads, xr = xr_base + e;
+            unsigned long long c = 0ull;
+            unsigned pix = 0xffffffffu;                 // marker: outside the image
+            if (e >= 0 && e < span && xr >= 0 && xr < dm.W) {
+                c = __ldg(cen_r + row + xr);
+                pix = __ldg(right + row + xr);
             }
-            if (xa + 4 * g + i < xb)
-                *reinterpret_cast<float4*>(vrow + (size_t)(4 * g + i) * dm.Dp + 4 * q) = make_float4(out[0], out[1], out[2], out[3]);
+            s_rb[i] = pix; s_rl[i] = (unsigned)c; s_rh[i] = (unsigned)(c >> 32);
+        }
+        for (int i = threadIdx.x; i < Lx; i += blockDim.x) {
+            unsigned long long c = 0ull;
+            unsigned pix = 0u;
+            if (xa + i < xb) { c = __ldg(cen_l + row + xa + i); pix = __ldg(left + row + xa + i); }
+            s_lb[i] = pix; s_ll[i] = (unsigned)c; s_lh[i] = (unsigned)(c >> 32);
+        }
+        __syncthreads();
+        float* vrow = vol + (size_t)pair * dm.vol_stride + ((size_t)row + xa) * dm.Dp;
+        for (int g = g0; g < (g0 < gpc ? ngroups : 0); g += gpc) {
+            // block (i, j): entry e0 + 3 - j + i with e0 = 4g + D - 4 - 4q >= -3; position e0 + pads is a multiple of 4
+            const int p0 = 4 * g + dm.D - 4 - 4 * q + pads;
+            const uint4 b0 = *reinterpret_cast<const uint4*>(s_rb + p0), b1 = *reinterpret_cast<const uint4*>(s_rb + p0 + 4);
+            const uint4 l0 = *reinterpret_cast<const uint4*>(s_rl + p0), l1 = *reinterpret_cast<const uint4*>(s_rl + p0 + 4);
+            const uint4 h0 = *reinterpret_cast<const uint4*>(s_rh + p0), h1 = *reinterpret_cast<const uint4*>(s_rh + p0 + 4);
+            const uint4 cb = *reinterpret_cast<const uint4*>(s_lb + 4 * g), cl = *reinterpret_cast<const uint4*>(s_ll + 4 * g),
+                        ch = *reinterpret_cast<const uint4*>(s_lh + 4 * g);
+            const unsigned rb[7] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z};
+            const unsigned rl[7] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z};
+            const unsigned rh[7] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z};
+            const unsigned lb[4] = {cb.x, cb.y, cb.z, cb.w}, ll[4] = {cl.x, cl.y, cl.z, cl.w}, lh[4] = {ch.x, ch.y, ch.z, ch.w};
+    #pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float out[4];
+    #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    // branch-free: padding disparities (di >= D) and out-of-image matches compute on whatever the entry holds and
+                    // are overwritten by selects -- the per-disparity branches used to cost more than the arithmetic
+                    const int c = 3 - j + i;
+                    const int sad = min((int)__vsadu4(lb[i], rb[c]), 765);     // |dB| + |dG| + |dR| (4th byte is 0 in both; the marker clamps)
+                    const int ham = (__popc(ll[i] ^ rl[c]) + __popc(lh[i] ^ rh[c])) & 63;
+                    float v = __fsub_rn(t_ad[sad * CV_AD_REP], t_ce[ham * 32]);
+                    v = rb[c] == 0xffffffffu ? 1.0f : v;                        // out-of-image match: cost_computor.cpp:101-104
+                    out[j] = (EXACT || 4 * q + j < dm.D) ? v : 0.0f;            // padding disparity, never read as a cost
+                }
+                if (xa + 4 * g + i < xb)
+                    *reinterpret_cast<float4*>(vrow + (size_t)(4 * g + i) * dm.Dp + 4 * q) = make_float4(out[0], out[1], out[2], out[3]);
+            }
         }
     }
 }
@@ -201,9 +209,10 @@ void adc_launch_cost(const AdcParams& P, const AdcWave& w, float* vol, cudaStrea
         cudaFuncSetAttribute(k_cost_volume<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         adc_once_done(attr_once);
     }
-    dim3 grid(P.dm.H * nseg, w.S);
-    if (P.dm.D == P.dm.Dp) k_cost_volume<true><<<grid, threads, smem, st>>>(P.dm, gpc, nseg, Lx, w.bgrx, w.census, vol, w.lut_ad, w.lut_cen);
-    else k_cost_volume<false><<<grid, threads, smem, st>>>(P.dm, gpc, nseg, Lx, w.bgrx, w.census, vol, w.lut_ad, w.lut_cen);
+    const int rpc = 4;                              // rows per CTA: the 57 KB of tables are staged once per four rows
+    dim3 grid((P.dm.H + rpc - 1) / rpc * nseg, w.S);
+    if (P.dm.D == P.dm.Dp) k_cost_volume<true><<<grid, threads, smem, st>>>(P.dm, gpc, nseg, Lx, rpc, w.bgrx, w.census, vol, w.lut_ad, w.lut_cen);
+    else k_cost_volume<false><<<grid, threads, smem, st>>>(P.dm, gpc, nseg, Lx, rpc, w.bgrx, w.census, vol, w.lut_ad, w.lut_cen);
     ++*launches;
 }
 

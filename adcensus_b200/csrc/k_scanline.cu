@@ -199,6 +199,10 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
            const unsigned* __restrict__ rec, int sx, int sy) {
     constexpr int PF = SO_PF;
     constexpr int LPW = 32 / LPS;               // lines per warp
+    // SWZ: a lane's eight costs are two 16-byte chunks 32 bytes apart, so the eight lanes of a 128-bit load phase would hit
+    // four bank groups twice; the cp.async fill therefore stores chunk c at position c ^ ((c >> 3) & 1) and the two loads of
+    // lane gl read positions 2gl + b and 2gl + 1 - b, b = (gl >> 2) & 1: eight different bank groups per phase.
+    constexpr bool SWZ = FULL && K == 8 && !BULK;
     extern __shared__ __align__(16) unsigned char so_smem[];
     const AdcDims& dm = P.dm;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -268,7 +272,7 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
         const long long p = (long long)y0 * W + x0 + (long long)step * pstep;
         const float* cs = S + (size_t)p * Dp;
         const unsigned* rs = R + (size_t)p * nrec;
-        for (int c = gl; c < cost_chunks; c += LPS) cp_async16(slot + cost_off + c * 16, cs + c * 4);
+        for (int c = gl; c < cost_chunks; c += LPS) cp_async16(slot + cost_off + (SWZ ? (c ^ ((c >> 3) & 1)) : c) * 16, cs + c * 4);
         for (int c = gl; c < rec_chunks; c += LPS) cp_async16(slot + rec_off + c * 16, rs + c * 4);
     };
 
@@ -311,7 +315,13 @@ k_scanline(AdcParams P, const float* __restrict__ src, float* __restrict__ dst,
         }
         const unsigned char* slot = wring + (size_t)(step % PF) * LPW * slot_bytes;
         float C[K];
-        ld_vec<K>(reinterpret_cast<const float*>(slot + cost_off), gl, Dp, C);
+        if (SWZ) {
+            const int b = (gl >> 2) & 1;
+            const float4 c0 = *reinterpret_cast<const float4*>(slot + cost_off + (2 * gl + b) * 16);
+            const float4 c1 = *reinterpret_cast<const float4*>(slot + cost_off + (2 * gl + 1 - b) * 16);
+            C[0] = c0.x; C[1] = c0.y; C[2] = c0.z; C[3] = c0.w;
+            C[4 % K] = c1.x; C[5 % K] = c1.y; C[6 % K] = c1.z; C[7 % K] = c1.w;
+        } else ld_vec<K>(reinterpret_cast<const float*>(slot + cost_off), gl, Dp, C);
         const unsigned* rw = reinterpret_cast<const unsigned*>(slot + rec_off);
         const bool a1 = rw[0] != 0u;
         const unsigned bits = __funnelshift_r(rw[1 + (bit0 >> 5)], rw[2 + (bit0 >> 5)], bit0 & 31);

@@ -23,7 +23,7 @@ __device__ __forceinline__ float adc_subpixel(float c1, float c2, float cmin, in
 // carrying (minimum, argmin) in registers from chunk to chunk: three instructions per cost.  A column outside the image
 // is Large_Float: never the minimum (the running minimum starts there).  The two parabola neighbours of each minimum
 // are fetched afterwards (four L2 hits per pixel), Large_Float where the reference's cost_local holds it (:277-286).
-// Shared memory per CTA is independent of the disparity range (17 KB), so the kernel keeps six CTAs per SM at D = 64
+// Shared memory per CTA is independent of the disparity range (18 KB), so the kernel keeps six CTAs per SM at D = 64
 // as at D = 256 -- the first version staged (WT_PX + D - 1) whole columns, 172 KB for a 64-thread CTA at D = 192.
 // The right tile's columns are the left tile of the neighbouring CTAs: they come out of L2.
 // ---------------------------------------------------------------------------------------------
@@ -32,11 +32,13 @@ __device__ __forceinline__ float adc_subpixel(float c1, float c2, float cmin, in
 #define WT_LS (WT_DC + 4)      // row stride of the left tile: rows stay 16-byte aligned (128-bit stores and loads), and the
                                // eight threads of a 128-bit load phase hit eight different 16-byte bank groups (20 t mod 32)
 #define WT_RT ((WT_PX + WT_DC - 1 + WT_PX / 4 - 1) / (WT_PX / 4))   // staging trips of the right tile (32 columns per trip)
+#define WT_RS (WT_PX + 3)      // row stride of the right tile: the skewed stores of a warp (columns cj .. cj + 7, four quads) land in 32
+                               // different banks: bank = cj + 8 kq + const (with stride 128 it is cj - 4 kq: pairs of lanes collide)
 
 __global__ void __launch_bounds__(WT_PX, 6)
 k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, float* __restrict__ disp_r) {
     __shared__ __align__(16) float tl[WT_PX * WT_LS];
-    __shared__ float tr[WT_DC * WT_PX];
+    __shared__ float tr[WT_DC * WT_RS];
     const int pair = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * WT_PX;
     const int W = dm.W, D = dm.D, Dp = dm.Dp;
     const float* rowv = vol + (size_t)pair * dm.vol_stride + (size_t)y * W * Dp;
@@ -76,7 +78,7 @@ k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, flo
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 const int r = r0 - c;
-                if (r >= 0 && r < WT_PX) tr[(4 * kq + c) * WT_PX + r] = e[c];
+                if (r >= 0 && r < WT_PX) tr[(4 * kq + c) * WT_RS + r] = e[c];
             }
         }
         __syncthreads();
@@ -92,14 +94,14 @@ k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, flo
                 const float a[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const float b = pr[(k4 + j) * WT_PX];
+                    const float b = pr[(k4 + j) * WT_RS];
                     if (lbest > a[j]) { lbest = a[j]; lk = k4 + j; }
                     if (rbest > b) { rbest = b; rk = k4 + j; }
                 }
             }
         } else {
             for (int k = 0; k < dn; k++) {
-                const float a = pl[k], b = pr[k * WT_PX];
+                const float a = pl[k], b = pr[k * WT_RS];
                 if (lbest > a) { lbest = a; lk = k; }
                 if (rbest > b) { rbest = b; rk = k; }
             }
