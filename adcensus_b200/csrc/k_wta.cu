@@ -23,14 +23,15 @@ __device__ __forceinline__ float adc_subpixel(float c1, float c2, float cmin, in
 // carrying (minimum, argmin) in registers from chunk to chunk: three instructions per cost.  A column outside the image
 // is Large_Float: never the minimum (the running minimum starts there).  The two parabola neighbours of each minimum
 // are fetched afterwards (four L2 hits per pixel), Large_Float where the reference's cost_local holds it (:277-286).
-// Shared memory per CTA is independent of the disparity range (18 KB), so the kernel keeps six CTAs per SM at D = 64
+// Shared memory per CTA is independent of the disparity range (16 KB), so the kernel keeps six CTAs per SM at D = 64
 // as at D = 256 -- the first version staged (WT_PX + D - 1) whole columns, 172 KB for a 64-thread CTA at D = 192.
 // The right tile's columns are the left tile of the neighbouring CTAs: they come out of L2.
 // ---------------------------------------------------------------------------------------------
 #define WT_PX 128
 #define WT_DC 16
-#define WT_LS (WT_DC + 4)      // row stride of the left tile: rows stay 16-byte aligned (128-bit stores and loads), and the
-                               // eight threads of a 128-bit load phase hit eight different 16-byte bank groups (20 t mod 32)
+#define WT_LS WT_DC            // row stride of the left tile; quad k of column t is stored at quad k ^ ((t >> 1) & 3): the eight
+                               // threads of a 128-bit phase -- eight columns x one quad when scanning, two columns x four quads when
+                               // staging -- hit eight different 16-byte bank groups
 #define WT_RT ((WT_PX + WT_DC - 1 + WT_PX / 4 - 1) / (WT_PX / 4))   // staging trips of the right tile (32 columns per trip)
 #define WT_RS (WT_PX + 3)      // row stride of the right tile: the skewed stores of a warp (columns cj .. cj + 7, four quads) land in 32
                                // different banks: bank = cj + 8 kq + const (with stride 128 it is cj - 4 kq: pairs of lanes collide)
@@ -69,7 +70,7 @@ k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, flo
         const int dn = min(WT_DC, D - d0);
 #pragma unroll
         for (int i = 0; i < WT_PX / 32; i++) {
-            *reinterpret_cast<float4*>(tl + (cj + 32 * i) * WT_LS + 4 * kq) = vl[i];
+            *reinterpret_cast<float4*>(tl + (cj + 32 * i) * WT_LS + 4 * (kq ^ ((cj >> 1) & 3))) = vl[i];
         }
 #pragma unroll
         for (int i = 0; i < WT_RT; i++) {               // element k of tile column j belongs to right pixel r = j - k
@@ -85,12 +86,13 @@ k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, flo
         if (d0 + WT_DC < D) fetch(d0 + WT_DC);
         // ---- scans: thread t = left pixel x0 + t and right pixel x0 + t; indices relative to the chunk
         const float* pl = tl + t * WT_LS;
+        const int sw = ((t >> 1) & 3) << 2;             // this column's quad swizzle, as a word offset
         const float* pr = tr + t;
         int lk = -1, rk = -1;
         if (dn == WT_DC) {
 #pragma unroll
             for (int k4 = 0; k4 < WT_DC; k4 += 4) {
-                const float4 a4 = *reinterpret_cast<const float4*>(pl + k4);
+                const float4 a4 = *reinterpret_cast<const float4*>(pl + (k4 ^ sw));
                 const float a[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -101,7 +103,7 @@ k_wta(AdcDims dm, const float* __restrict__ vol, float* __restrict__ disp_l, flo
             }
         } else {
             for (int k = 0; k < dn; k++) {
-                const float a = pl[k], b = pr[k * WT_RS];
+                const float a = pl[k ^ sw], b = pr[k * WT_RS];
                 if (lbest > a) { lbest = a; lk = k; }
                 if (rbest > b) { rbest = b; rk = k; }
             }
