@@ -506,7 +506,7 @@ int adc_create(int32_t width, int32_t height, const adc_option* opt, const adc_c
     if (height > ADC_MAX_HEIGHT)
         return fail(ADC_ERR_UNSUPPORTED, "adc_create: image height %d > %d is not supported (in-place median: one CTA per image)", height, ADC_MAX_HEIGHT);
     if (width > ADC_MAX_WIDTH || width + drange > ADC_MAX_WIDTH)
-        return fail(ADC_ERR_UNSUPPORTED, "adc_create: image width %d (+ disparity range %d) > %d is not supported (cost kernel stages a right-image row in shared memory)", width, drange, ADC_MAX_WIDTH);
+        return fail(ADC_ERR_UNSUPPORTED, "adc_create: image width %d (+ disparity range %d) > %d is not supported (widest size the kernels are validated for)", width, drange, ADC_MAX_WIDTH);
 
     adc_engine* e = new adc_engine();
     e->W = width; e->H = height; e->opt = *opt;
